@@ -1,0 +1,139 @@
+/*
+ * arvc_icp.h — C-ABI of the B200-native ICP scan-matching engine (libarvc_icp.so).
+ *
+ * Drop-in boundary for the hot path of JudithV/LIDAR_SLAM_ARVC.  The reference has no FFI layer of its
+ * own: its registration API is the Python classes keyframemanager.KeyFrame / KeyFrameManager, which call
+ * Open3D (CPU).  Each entry point below names the reference call it replaces (paths relative to the
+ * reference tree).  Plain pointers and sizes only; all arrays are host memory unless stated; row-major.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (ARVC_E_*); arvc_last_error() gives the text;
+ *   - a context owns one CUDA device + one stream; calls on one context must be serialised by the caller;
+ *   - scan ids are caller-chosen 64-bit keys (the Python host uses the index in KeyFrameManager.keyframes);
+ *   - "cloud order" of a preprocessed scan = order of `pointcloud_filtered.points` in the reference:
+ *       filter-stable order when voxel_size is off, ascending voxel key (ix,iy,iz) when it is on;
+ *     all indices that cross this boundary (correspondences, normals, points) are in cloud order;
+ *   - there is NO CPU fallback: without a CUDA device arvc_ctx_create fails.
+ */
+#ifndef ARVC_ICP_H
+#define ARVC_ICP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct arvc_ctx arvc_ctx;
+
+enum {
+    ARVC_OK = 0,
+    ARVC_E_CUDA = -1,      /* a CUDA runtime call failed */
+    ARVC_E_ARG = -2,       /* bad argument (null pointer, unknown scan id, bad method, ...) */
+    ARVC_E_STATE = -3,     /* scan not uploaded / not preprocessed / normals missing for point-to-plane */
+    ARVC_E_CAPACITY = -4,  /* device-side capacity exceeded (hash grid overflow, voxel index range) */
+    ARVC_E_NOMEM = -5
+};
+
+enum { ARVC_P2P = 0, ARVC_P2PLANE = 1 };
+
+/* --- context --------------------------------------------------------------------------------------- */
+int arvc_ctx_create(int device, arvc_ctx** out);
+void arvc_ctx_destroy(arvc_ctx* ctx);
+const char* arvc_last_error(const arvc_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+int arvc_sync(arvc_ctx* ctx);                     /* wait for all queued work of the context */
+void* arvc_stream(arvc_ctx* ctx);                 /* the context's cudaStream_t (for event timing) */
+int arvc_version(void);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t arvc_kernel_launches(const arvc_ctx* ctx);
+
+/* --- scans -----------------------------------------------------------------------------------------
+ * Replaces KeyFrame.load_pointcloud's result handed to Open3D (keyframemanager/keyframe.py:41-45): the
+ * PCD payload (float32 xyz, n points, NaNs allowed) is copied to the device.  Re-uploading an id replaces it.
+ * The _f64 variant is for PCD files with double fields.  Asynchronous w.r.t. the host when `xyz` is pinned. */
+int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n);
+int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n);
+/* KeyFrame.unload_pointcloud (keyframe.py:61-72): drop every device buffer of the scan. */
+int arvc_scan_free(arvc_ctx* ctx, int64_t scan_id);
+
+typedef struct arvc_preprocess_params {
+    /* KeyFrame.filter_radius_height (keyframe.py:74-94): keep r2=x*x+y*y with
+     *   r2 < max_radius2 && r2 > min_radius2 && z > min_height && z < max_height   (strict, float64).
+     * The radii arrive already squared: Python computes `radius ** 2` exactly as keyframe.py:92 does. */
+    double min_radius2, max_radius2, min_height, max_height;
+    /* voxel_down_sample (keyframe.py:111,151,159): <= 0 or NaN means "voxel_size is None". */
+    double voxel_size;
+    /* estimate_normals(KDTreeSearchParamHybrid(radius, max_nn)) (keyframe.py:160-162); want_normals = 0
+     * for 'icppointpoint' preprocessing (keyframe.py:148-151). */
+    double normal_radius;
+    int32_t max_nn;
+    int32_t want_normals;
+    /* hash-grid hints (0 = defaults): finest cell edge in metres; largest search distance the grid must
+     * be able to answer exactly (the ICP max_correspondence_distance, icp_parameters.yaml:22). */
+    double grid_cell;
+    double grid_max_dist;
+} arvc_preprocess_params;
+
+/* KeyFrame.pre_process (keyframe.py:113-162) for a batch of uploaded scans: filter -> [voxel] -> spatial
+ * sort + hash grid -> [normals].  Queued on the context stream; no host synchronisation. */
+int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p);
+
+/* Sizes after preprocessing (synchronises): raw, after filter, final cloud size; has_normals. */
+int arvc_scan_info(arvc_ctx* ctx, int64_t scan_id, int* n_raw, int* n_filtered, int* n_points, int* has_normals);
+/* np.asarray(pointcloud_filtered.points / .normals): xyz[n_points*3], normals[n_points*3] (NULL to skip), cloud order. */
+int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* normals);
+/* Parity taps.  raw_index[n_filtered]: raw indices kept by the filter, ascending.
+ * voxel keys[n_points*3] (Open3D voxel index per output point) and counts[n_points]; voxel mode only.
+ * nn_count[n_points]: number of neighbours used by the normal of each point (after the k / radius cut). */
+int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index);
+int arvc_scan_get_voxels(arvc_ctx* ctx, int64_t scan_id, int32_t* keys, int32_t* counts);
+int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count);
+
+/* --- registration ---------------------------------------------------------------------------------- */
+typedef struct arvc_icp_params {
+    double max_corr_dist; /* ICP_PARAMETERS.distance_threshold, config/icp_parameters.yaml:22 (10.0) */
+    double rel_fitness;   /* Open3D ICPConvergenceCriteria defaults, because keyframe.py:246-252 passes none: 1e-6 */
+    double rel_rmse;      /* 1e-6 */
+    int32_t max_iter;     /* 30 */
+    int32_t method;       /* ARVC_P2P: TransformationEstimationPointToPoint (keyframe.py:248);
+                             ARVC_P2PLANE: TransformationEstimationPointToPlane (keyframe.py:252) */
+} arvc_icp_params;
+
+/* KeyFrameManager.compute_transformation(i, j, Tij) (keyframemanager/keyframemanager.py:52-75) ->
+ * KeyFrame.local_registration_simple (keyframe.py:231-260) -> o3d registration_icp(source = scan j,
+ * target = scan i, threshold, init, estimation), for n_pairs independent pairs in one call.
+ *   tgt_ids[p] = scan i (target), src_ids[p] = scan j (source), init_T[16*p..] = Tij.array (row-major).
+ * Outputs (host): out_T[16*p..] = reg.transformation, fitness[p], rmse[p] = reg.fitness / reg.inlier_rmse,
+ *   updates[p] = ICP iterations executed, n_corr[p] = len(reg.correspondence_set).  Any may be NULL.
+ * The whole iteration (correspondence search, residual/Jacobian reduction, 6x6 solve or Umeyama,
+ * convergence test) runs on the device; the call synchronises once at the end to deliver the results. */
+int arvc_icp_batch(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
+                   const arvc_icp_params* p, double* out_T, double* fitness, double* rmse, int32_t* updates,
+                   int32_t* n_corr);
+
+/* Same, asynchronous: results stay on the device until arvc_icp_batch_finish; lets the host overlap the
+ * upload of the next batch.  Records are 160 bytes: { int32 pair, updates, n_corr, passes; double T[16]; fitness; rmse }. */
+typedef struct arvc_result_record {
+    int32_t pair, updates, n_corr, passes;
+    double T[16];
+    double fitness, rmse;
+} arvc_result_record;
+int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
+                         const arvc_icp_params* p, uint64_t* ticket);
+int arvc_icp_batch_finish(arvc_ctx* ctx, uint64_t ticket, arvc_result_record* records /* [n_pairs] host */);
+
+/* Parity tap: one pair, recording every pass.  corr[pass*n_src + i] = target index (cloud order) matched to
+ * source point i (cloud order) in that pass or -1; trace_T[pass*16..] = transformation the pass was evaluated
+ * at; trace_fitness/rmse[pass].  Arrays sized for (max_iter+1) passes; n_passes receives the count. */
+int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* init_T, const arvc_icp_params* p,
+                   int32_t* corr, double* trace_T, double* trace_fitness, double* trace_rmse, int32_t* n_passes,
+                   arvc_result_record* result);
+
+/* pinned host staging (optional; plain malloc'ed pointers work too, just slower for H2D) */
+void* arvc_host_alloc(size_t bytes);
+void arvc_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARVC_ICP_H */

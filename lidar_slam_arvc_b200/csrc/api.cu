@@ -1,0 +1,655 @@
+// C-ABI of the engine (include/arvc_icp.h): context, scan store, batch orchestration.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/arvc_icp.h"
+#include "engine.cuh"
+
+using namespace arvc;
+
+namespace {
+
+std::string g_create_error;
+
+struct Scan {
+    int64_t id = 0;
+    int n_raw = 0;
+    bool f64 = false;
+    void* d_raw = nullptr;
+    // persistent slab
+    void* slab = nullptr;
+    size_t slab_bytes = 0;
+    ScanDev dev{};              // host copy (persistent pointers only)
+    ScanDev* d_dev = nullptr;   // device copy used by the ICP kernels
+    bool preprocessed = false;
+    bool has_normals = false;
+    bool voxel_on = false;
+    arvc_preprocess_params params{};
+};
+
+struct PendingBatch {
+    int n_pairs = 0;
+    void* slab = nullptr;
+    PairState* d_states = nullptr;
+    PairState* h_states = nullptr;   // pinned, from the context's pool
+    size_t h_bytes = 0;
+};
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct SlabPlanner {   // two-pass bump allocator: plan sizes, then hand out pointers
+    size_t off = 0;
+    char* base = nullptr;
+    template <typename T> T* take(size_t count) {
+        const size_t o = off;
+        off += align_up(count * sizeof(T));
+        return base ? reinterpret_cast<T*>(base + o) : nullptr;
+    }
+};
+
+}  // namespace
+
+struct arvc_ctx {
+    int device = 0;
+    Launcher L;
+    std::string error;
+    std::unordered_map<int64_t, std::unique_ptr<Scan>> scans;
+    std::map<uint64_t, PendingBatch> pending;
+    uint64_t next_ticket = 1;
+    std::vector<std::pair<size_t, void*>> pinned_free;   // recycled pinned staging buffers
+
+    void* pinned_get(size_t bytes, size_t* got) {
+        for (size_t i = 0; i < pinned_free.size(); ++i)
+            if (pinned_free[i].first >= bytes) {
+                void* p = pinned_free[i].second;
+                *got = pinned_free[i].first;
+                pinned_free.erase(pinned_free.begin() + i);
+                return p;
+            }
+        size_t cap = 1 << 16;
+        while (cap < bytes) cap <<= 1;
+        void* p = nullptr;
+        if (cudaMallocHost(&p, cap) != cudaSuccess) return nullptr;
+        *got = cap;
+        return p;
+    }
+    void pinned_put(void* p, size_t bytes) { if (p) pinned_free.emplace_back(bytes, p); }
+
+    int fail(int code, const std::string& msg) { error = msg; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        error = buf;
+        return ARVC_E_CUDA;
+    }
+    Scan* find(int64_t id) {
+        auto it = scans.find(id);
+        return it == scans.end() ? nullptr : it->second.get();
+    }
+};
+
+#define CK(call)                                                      \
+    do {                                                              \
+        const cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return ctx->cuda_fail(e__, #call);    \
+    } while (0)
+
+namespace {
+
+void release_scan(arvc_ctx* ctx, Scan* s) {
+    cudaStream_t st = ctx->L.stream;
+    if (s->d_raw) cudaFreeAsync(s->d_raw, st);
+    if (s->slab) cudaFreeAsync(s->slab, st);
+    if (s->d_dev) cudaFreeAsync(s->d_dev, st);
+    s->d_raw = s->slab = nullptr;
+    s->d_dev = nullptr;
+}
+
+bool same_params(const arvc_preprocess_params& a, const arvc_preprocess_params& b) {
+    auto eq = [](double x, double y) { return x == y || (x != x && y != y); };
+    const bool va = a.voxel_size > 0, vb = b.voxel_size > 0;
+    return eq(a.min_radius2, b.min_radius2) && eq(a.max_radius2, b.max_radius2) && eq(a.min_height, b.min_height) &&
+           eq(a.max_height, b.max_height) && va == vb && (!va || eq(a.voxel_size, b.voxel_size)) &&
+           eq(a.grid_cell, b.grid_cell) && eq(a.grid_max_dist, b.grid_max_dist);
+}
+
+int bits_for(double cells) {
+    int b = 1;
+    while (b < 31 && (double)(1ll << b) < cells) ++b;
+    return b;
+}
+
+int upload(arvc_ctx* ctx, int64_t id, const void* xyz, int n, bool f64) {
+    if (!ctx) return ARVC_E_ARG;
+    if (n < 0 || (n > 0 && !xyz)) return ctx->fail(ARVC_E_ARG, "scan_upload: bad pointer/size");
+    CK(cudaSetDevice(ctx->device));
+    Scan* old = ctx->find(id);
+    if (old) { release_scan(ctx, old); ctx->scans.erase(id); }
+    auto s = std::make_unique<Scan>();
+    s->id = id; s->n_raw = n; s->f64 = f64;
+    const size_t bytes = (size_t)n * 3 * (f64 ? sizeof(double) : sizeof(float));
+    if (n > 0) {
+        CK(cudaMallocAsync(&s->d_raw, bytes, ctx->L.stream));
+        CK(cudaMemcpyAsync(s->d_raw, xyz, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+    }
+    ctx->scans[id] = std::move(s);
+    return ARVC_OK;
+}
+
+// device buffers that outlive preprocessing
+void plan_persistent(SlabPlanner& P, Scan& s, bool wide, bool voxel_on, unsigned table_cap) {
+    const size_t cap = (size_t)std::max(s.n_raw, 1);
+    ScanDev& d = s.dev;
+    d.counts = P.take<int>(CNT_WORDS);
+    d.recs = wide ? (void*)P.take<RecD>(cap) : (void*)P.take<RecF>(cap);
+    d.normals = P.take<double>(cap * 4);
+    d.nn_count = P.take<int>(cap);
+    d.table = P.take<HashEntry>(table_cap);
+    d.raw_index = P.take<int>(cap);
+    d.vox_keys = voxel_on ? P.take<int>(cap * 3) : nullptr;
+    d.vox_counts = voxel_on ? P.take<int>(cap) : nullptr;
+}
+
+void plan_scratch(SlabPlanner& P, ScanDev& d, int n_raw, bool voxel_on) {
+    const size_t cap = (size_t)std::max(n_raw, 1);
+    d.fx = P.take<double>(cap); d.fy = P.take<double>(cap); d.fz = P.take<double>(cap);
+    if (voxel_on) {
+        d.vx = P.take<double>(cap); d.vy = P.take<double>(cap); d.vz = P.take<double>(cap);
+        d.key64[0] = P.take<unsigned long long>(cap); d.key64[1] = P.take<unsigned long long>(cap);
+    } else {
+        d.vx = d.vy = d.vz = nullptr;
+        d.key64[0] = d.key64[1] = nullptr;
+    }
+    d.key32[0] = P.take<unsigned>(cap); d.key32[1] = P.take<unsigned>(cap);
+    d.val[0] = P.take<int>(cap); d.val[1] = P.take<int>(cap);
+    d.hist = P.take<int>(256 * ((cap + 2047) / 2048));
+    d.blk = P.take<int>((cap + 1023) / 1024 + 8);
+    d.bbox = P.take<double>(8);
+}
+
+__global__ void k_clear_scan(const ScanDev* __restrict__ scans) {
+    const ScanDev& s = scans[blockIdx.y];
+    const unsigned cap = s.table_mask + 1u;
+    uint4* t = reinterpret_cast<uint4*>(s.table);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) t[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < CNT_WORDS) s.counts[threadIdx.x] = 0;
+        if (threadIdx.x < 8) reinterpret_cast<unsigned long long*>(s.bbox)[threadIdx.x] = 0xffffffffffffffffULL;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int arvc_version(void) { return 100; }
+
+int arvc_ctx_create(int device, arvc_ctx** out) {
+    if (!out) return ARVC_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU fallback";
+        return ARVC_E_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "bad device index"; return ARVC_E_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ARVC_E_CUDA; }
+    auto ctx = new arvc_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ARVC_E_CUDA; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return ARVC_OK;
+}
+
+void arvc_ctx_destroy(arvc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->pending) {
+        if (kv.second.slab) cudaFreeAsync(kv.second.slab, ctx->L.stream);
+        if (kv.second.h_states) cudaFreeHost(kv.second.h_states);
+    }
+    for (auto& pf : ctx->pinned_free) cudaFreeHost(pf.second);
+    for (auto& kv : ctx->scans) release_scan(ctx, kv.second.get());
+    cudaStreamSynchronize(ctx->L.stream);
+    cudaStreamDestroy(ctx->L.stream);
+    delete ctx;
+}
+
+const char* arvc_last_error(const arvc_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int arvc_sync(arvc_ctx* ctx) {
+    if (!ctx) return ARVC_E_ARG;
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
+    return ARVC_OK;
+}
+
+void* arvc_stream(arvc_ctx* ctx) { return ctx ? (void*)ctx->L.stream : nullptr; }
+int64_t arvc_kernel_launches(const arvc_ctx* ctx) { return ctx ? ctx->L.launches : 0; }
+
+int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n) { return upload(ctx, scan_id, xyz, n, false); }
+int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n) { return upload(ctx, scan_id, xyz, n, true); }
+
+int arvc_scan_free(arvc_ctx* ctx, int64_t scan_id) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s) return ARVC_OK;
+    cudaSetDevice(ctx->device);
+    release_scan(ctx, s);
+    ctx->scans.erase(scan_id);
+    return ARVC_OK;
+}
+
+int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p) {
+    if (!ctx) return ARVC_E_ARG;
+    if (n_scans < 0 || (n_scans > 0 && !scan_ids) || !p) return ctx->fail(ARVC_E_ARG, "scan_preprocess: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const bool voxel_on = p->voxel_size > 0.0;          // NaN and <= 0 mean "voxel_size is None"
+    const bool want_normals = p->want_normals != 0;
+    if (!(p->max_radius2 > 0) || !std::isfinite(p->max_radius2) || !std::isfinite(p->min_height) || !std::isfinite(p->max_height) ||
+        !(p->max_height > p->min_height))
+        return ctx->fail(ARVC_E_ARG, "scan_preprocess: the radius/height filter must be bounded (finite max_radius, min/max_height)");
+    if (want_normals && (!(p->normal_radius > 0) || p->max_nn < 1)) return ctx->fail(ARVC_E_ARG, "scan_preprocess: bad normal parameters");
+
+    // ---- grid specification from the filter bounds (data independent, so no device->host round trip)
+    const double R = std::sqrt(p->max_radius2);
+    const double pad = 0.5;
+    const double ext = std::max(2 * (R + pad), p->max_height - p->min_height + 2 * pad);
+    double c0 = p->grid_cell > 0 ? p->grid_cell : 0.15;
+    const double ncell_max = (double)((1 << kMortonBits) - 1);
+    if (ext / c0 > ncell_max) c0 = ext / ncell_max;
+    const double max_dist = p->grid_max_dist > 0 ? p->grid_max_dist : 10.0;
+    GridSpec g{};
+    g.ox = -(R + pad); g.oy = -(R + pad); g.oz = p->min_height - pad;
+    g.c0 = c0; g.inv_c0 = 1.0 / c0;
+    g.top_level = 0;
+    while (g.top_level < kMortonBits && c0 * (double)(1 << g.top_level) < max_dist * 1.001) ++g.top_level;
+    g.cold_level = std::min(1, g.top_level);
+    NormalParams np{};
+    np.radius = p->normal_radius; np.max_nn = p->max_nn; np.level = 0;
+    if (want_normals)
+        while (np.level < kMortonBits && c0 * (double)(1 << np.level) < p->normal_radius * (1.0 + 1e-6)) ++np.level;
+
+    VoxelParams vp{};
+    if (voxel_on) {
+        vp.voxel = p->voxel_size;
+        vp.bx = bits_for(2 * R / p->voxel_size + 3);
+        vp.by = vp.bx;
+        vp.bz = bits_for((p->max_height - p->min_height) / p->voxel_size + 3);
+        if (vp.bx + vp.by + vp.bz > 63) return ctx->fail(ARVC_E_ARG, "scan_preprocess: voxel_size too small for the filter extent");
+    }
+    FilterParams fp{p->min_radius2, p->max_radius2, p->min_height, p->max_height};
+
+    // ---- collect the scans that actually need work
+    std::vector<Scan*> todo, normals_only;
+    for (int i = 0; i < n_scans; ++i) {
+        Scan* s = ctx->find(scan_ids[i]);
+        if (!s) return ctx->fail(ARVC_E_STATE, "scan_preprocess: unknown scan id (upload first)");
+        bool dup = false;
+        for (Scan* t : todo) dup |= (t == s);
+        if (dup) continue;
+        if (s->preprocessed && same_params(s->params, *p)) {
+            if (!want_normals || (s->has_normals && s->params.normal_radius == p->normal_radius && s->params.max_nn == p->max_nn)) continue;
+        }
+        todo.push_back(s);
+    }
+    if (todo.empty()) return ARVC_OK;
+
+    // ---- allocate: persistent slab per scan, one scratch slab for the batch
+    int cap_max = 0;
+    bool any_wide = false, any_narrow = false;
+    std::vector<ScanDev> h_batch(todo.size());
+    SlabPlanner scratch_plan;
+    for (Scan* s : todo) {
+        const bool wide = s->f64 || voxel_on;
+        unsigned tcap = 1024;
+        while (tcap < 4u * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;
+        if (s->slab) { cudaFreeAsync(s->slab, ctx->L.stream); s->slab = nullptr; }
+        SlabPlanner pp;
+        plan_persistent(pp, *s, wide, voxel_on, tcap);
+        s->slab_bytes = pp.off;
+        CK(cudaMallocAsync(&s->slab, s->slab_bytes, ctx->L.stream));
+        SlabPlanner pq;
+        pq.base = reinterpret_cast<char*>(s->slab);
+        s->dev = ScanDev{};
+        plan_persistent(pq, *s, wide, voxel_on, tcap);
+        s->dev.raw = s->d_raw; s->dev.n_raw = s->n_raw; s->dev.raw_f64 = s->f64 ? 1 : 0; s->dev.cap = std::max(s->n_raw, 1);
+        s->dev.wide = wide ? 1 : 0; s->dev.table_mask = tcap - 1; s->dev.grid = g;
+        ScanDev tmp = s->dev;
+        plan_scratch(scratch_plan, tmp, s->n_raw, voxel_on);
+        cap_max = std::max(cap_max, s->n_raw);
+        any_wide |= wide; any_narrow |= !wide;
+    }
+    void* scratch = nullptr;
+    const size_t scratch_bytes = scratch_plan.off + align_up(sizeof(ScanDev) * todo.size());
+    CK(cudaMallocAsync(&scratch, scratch_bytes, ctx->L.stream));
+    SlabPlanner sp;
+    sp.base = reinterpret_cast<char*>(scratch);
+    for (size_t i = 0; i < todo.size(); ++i) {
+        h_batch[i] = todo[i]->dev;
+        plan_scratch(sp, h_batch[i], todo[i]->n_raw, voxel_on);
+    }
+    ScanDev* d_batch = sp.take<ScanDev>(todo.size());
+    CK(cudaMemcpyAsync(d_batch, h_batch.data(), sizeof(ScanDev) * todo.size(), cudaMemcpyHostToDevice, ctx->L.stream));
+
+    // ---- run
+    unsigned tmax = 0;
+    for (Scan* s : todo) tmax = std::max(tmax, s->dev.table_mask + 1u);
+    ctx->L.launch(k_clear_scan, dim3(std::min(256u, (tmax + 255u) / 256u), (unsigned)todo.size()), dim3(256), (const ScanDev*)d_batch);
+    run_preprocess(ctx->L, d_batch, (int)todo.size(), cap_max, fp, vp, voxel_on);
+    if (want_normals) run_normals(ctx->L, d_batch, (int)todo.size(), cap_max, np, any_wide, any_narrow);
+
+    // ---- publish the persistent device descriptors used by the ICP kernels
+    for (Scan* s : todo) {
+        if (!s->d_dev) CK(cudaMallocAsync(&s->d_dev, sizeof(ScanDev), ctx->L.stream));
+        CK(cudaMemcpyAsync(s->d_dev, &s->dev, sizeof(ScanDev), cudaMemcpyHostToDevice, ctx->L.stream));
+        s->preprocessed = true;
+        s->has_normals = want_normals;
+        s->voxel_on = voxel_on;
+        s->params = *p;
+    }
+    CK(cudaFreeAsync(scratch, ctx->L.stream));
+    if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
+    return ARVC_OK;
+}
+
+static int fetch_counts(arvc_ctx* ctx, Scan* s, int* counts) {
+    CK(cudaMemcpyAsync(counts, s->dev.counts, sizeof(int) * CNT_WORDS, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    if (counts[CNT_ERR] & ERR_HASH_FULL) return ctx->fail(ARVC_E_CAPACITY, "hash grid overflow");
+    if (counts[CNT_ERR] & ERR_VOXEL_RANGE) return ctx->fail(ARVC_E_CAPACITY, "voxel index outside the range implied by the filter bounds");
+    return ARVC_OK;
+}
+
+int arvc_scan_info(arvc_ctx* ctx, int64_t scan_id, int* n_raw, int* n_filtered, int* n_points, int* has_normals) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s) return ctx->fail(ARVC_E_STATE, "scan_info: unknown scan id");
+    CK(cudaSetDevice(ctx->device));
+    if (n_raw) *n_raw = s->n_raw;
+    if (has_normals) *has_normals = s->has_normals ? 1 : 0;
+    if (!s->preprocessed) {
+        if (n_filtered) *n_filtered = -1;
+        if (n_points) *n_points = -1;
+        return ARVC_OK;
+    }
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    if (n_filtered) *n_filtered = c[CNT_NFILT];
+    if (n_points) *n_points = c[CNT_NPTS];
+    return ARVC_OK;
+}
+
+int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* normals) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_get_points: scan not preprocessed");
+    if (normals && !s->has_normals) return ctx->fail(ARVC_E_STATE, "scan_get_points: no normals (point-to-point preprocessing)");
+    CK(cudaSetDevice(ctx->device));
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    const int n = c[CNT_NPTS];
+    if (n == 0) return ARVC_OK;
+    std::vector<double> hn;
+    std::vector<char> hr((size_t)n * (s->dev.wide ? sizeof(RecD) : sizeof(RecF)));
+    CK(cudaMemcpyAsync(hr.data(), s->dev.recs, hr.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    if (normals) {
+        hn.resize((size_t)n * 4);
+        CK(cudaMemcpyAsync(hn.data(), s->dev.normals, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    }
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (int p = 0; p < n; ++p) {
+        int idx;
+        double x, y, z;
+        if (s->dev.wide) { const RecD& r = reinterpret_cast<const RecD*>(hr.data())[p]; x = r.x; y = r.y; z = r.z; idx = r.idx; }
+        else { const RecF& r = reinterpret_cast<const RecF*>(hr.data())[p]; x = r.x; y = r.y; z = r.z; idx = r.idx; }
+        if (idx < 0 || idx >= n) return ctx->fail(ARVC_E_CUDA, "scan_get_points: corrupt permutation");
+        if (xyz) { xyz[3 * (size_t)idx] = x; xyz[3 * (size_t)idx + 1] = y; xyz[3 * (size_t)idx + 2] = z; }
+        if (normals) for (int d = 0; d < 3; ++d) normals[3 * (size_t)idx + d] = hn[4 * (size_t)p + d];
+    }
+    return ARVC_OK;
+}
+
+int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed || !raw_index) return ctx->fail(ARVC_E_STATE, "scan_get_filter_indices: scan not preprocessed");
+    CK(cudaSetDevice(ctx->device));
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    if (c[CNT_NFILT] > 0) {
+        CK(cudaMemcpyAsync(raw_index, s->dev.raw_index, sizeof(int) * c[CNT_NFILT], cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    return ARVC_OK;
+}
+
+int arvc_scan_get_voxels(arvc_ctx* ctx, int64_t scan_id, int32_t* keys, int32_t* counts) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed || !s->voxel_on) return ctx->fail(ARVC_E_STATE, "scan_get_voxels: scan not preprocessed with a voxel size");
+    CK(cudaSetDevice(ctx->device));
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    const int n = c[CNT_NPTS];
+    if (n > 0) {
+        if (keys) CK(cudaMemcpyAsync(keys, s->dev.vox_keys, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->L.stream));
+        if (counts) CK(cudaMemcpyAsync(counts, s->dev.vox_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    return ARVC_OK;
+}
+
+int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed || !s->has_normals || !nn_count) return ctx->fail(ARVC_E_STATE, "scan_get_nn_counts: no normals");
+    CK(cudaSetDevice(ctx->device));
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    const int n = c[CNT_NPTS];
+    if (n == 0) return ARVC_OK;
+    std::vector<int> hc(n);
+    std::vector<char> hr((size_t)n * (s->dev.wide ? sizeof(RecD) : sizeof(RecF)));
+    CK(cudaMemcpyAsync(hr.data(), s->dev.recs, hr.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(hc.data(), s->dev.nn_count, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    for (int p = 0; p < n; ++p) {
+        const int idx = s->dev.wide ? reinterpret_cast<const RecD*>(hr.data())[p].idx : reinterpret_cast<const RecF*>(hr.data())[p].idx;
+        nn_count[idx] = hc[p];
+    }
+    return ARVC_OK;
+}
+
+// ---- registration --------------------------------------------------------------------------------------
+static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
+                       const arvc_icp_params* p, bool trace, PendingBatch& pb, int** d_corr_trace, double** d_state_trace,
+                       int* src_cap_out) {
+    if (n_pairs < 0 || (n_pairs > 0 && (!tgt_ids || !src_ids || !init_T)) || !p) return ctx->fail(ARVC_E_ARG, "icp: bad arguments");
+    if (p->method != ARVC_P2P && p->method != ARVC_P2PLANE) return ctx->fail(ARVC_E_ARG, "icp: unknown method");
+    if (p->max_iter < 0) return ctx->fail(ARVC_E_ARG, "icp: max_iter < 0");
+    if (n_pairs > 32768) return ctx->fail(ARVC_E_ARG, "icp: at most 32768 pairs per call (split the batch)");
+    CK(cudaSetDevice(ctx->device));
+    pb.n_pairs = n_pairs;
+    if (n_pairs == 0) return ARVC_OK;
+    int combos = 0, src_cap_max = 1;
+    std::vector<Scan*> S(n_pairs), T(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) {
+        S[i] = ctx->find(src_ids[i]);
+        T[i] = ctx->find(tgt_ids[i]);
+        if (!S[i] || !T[i] || !S[i]->preprocessed || !T[i]->preprocessed) return ctx->fail(ARVC_E_STATE, "icp: scan not uploaded/preprocessed");
+        if (p->method == ARVC_P2PLANE && !T[i]->has_normals) return ctx->fail(ARVC_E_STATE, "icp: point-to-plane needs target normals");
+        const double need = p->max_corr_dist * 1.001;
+        const GridSpec& g = T[i]->dev.grid;
+        if (g.top_level < kMortonBits && g.c0 * (double)(1 << g.top_level) < need)
+            return ctx->fail(ARVC_E_STATE, "icp: target grid was built for a smaller max_corr_dist (set grid_max_dist at preprocess)");
+        combos |= 1 << (2 * S[i]->dev.wide + T[i]->dev.wide);
+        src_cap_max = std::max(src_cap_max, S[i]->dev.cap);
+    }
+    const int passes = p->max_iter + 1;
+    SlabPlanner plan;
+    for (int pass = 0; pass < 2; ++pass) {
+        SlabPlanner P;
+        P.base = pass ? reinterpret_cast<char*>(pb.slab) : nullptr;
+        PairDev* d_pairs = P.take<PairDev>(n_pairs);
+        PairState* d_states = P.take<PairState>(n_pairs);
+        std::vector<PairDev> hp(pass ? n_pairs : 0);
+        for (int i = 0; i < n_pairs; ++i) {
+            const size_t cap = (size_t)S[i]->dev.cap;
+            const size_t nblk = (cap + kIcpBlock - 1) / kIcpBlock;
+            double* partials = P.take<double>(nblk * kSumStride);
+            int* prev = P.take<int>(cap);
+            int* ct = trace ? P.take<int>(cap * passes) : nullptr;
+            double* stt = trace ? P.take<double>((size_t)passes * 18) : nullptr;
+            if (pass) {
+                hp[i].src = S[i]->d_dev; hp[i].tgt = T[i]->d_dev; hp[i].state = d_states + i;
+                hp[i].partials = partials; hp[i].prev = prev; hp[i].corr_trace = ct; hp[i].state_trace = stt;
+                if (trace && d_corr_trace) { *d_corr_trace = ct; *d_state_trace = stt; }
+            }
+        }
+        if (!pass) {
+            plan = P;
+            CK(cudaMallocAsync(&pb.slab, plan.off, ctx->L.stream));
+            if (trace) CK(cudaMemsetAsync(pb.slab, 0xff, plan.off, ctx->L.stream));   // untouched trace entries read as -1 / NaN
+        } else {
+            pb.d_states = d_states;
+            pb.h_states = reinterpret_cast<PairState*>(ctx->pinned_get(sizeof(PairState) * n_pairs, &pb.h_bytes));
+            if (!pb.h_states) return ctx->fail(ARVC_E_NOMEM, "icp: pinned host allocation failed");
+            std::memset(pb.h_states, 0, sizeof(PairState) * n_pairs);
+            for (int i = 0; i < n_pairs; ++i) std::memcpy(pb.h_states[i].T, init_T + 16 * (size_t)i, sizeof(double) * 16);
+            CK(cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
+            CK(cudaMemcpyAsync(d_states, pb.h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
+            IcpParams ip{};
+            ip.max_d = p->max_corr_dist;
+            ip.max_d2 = p->max_corr_dist > 0 ? p->max_corr_dist * p->max_corr_dist : 0.0;
+            ip.rel_fitness = p->rel_fitness; ip.rel_rmse = p->rel_rmse; ip.max_iter = p->max_iter; ip.method = p->method;
+            run_icp(ctx->L, d_pairs, n_pairs, src_cap_max, ip, combos);
+            CK(cudaMemcpyAsync(pb.h_states, d_states, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->L.stream));
+        }
+    }
+    if (src_cap_out) *src_cap_out = src_cap_max;
+    if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
+    return ARVC_OK;
+}
+
+static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec) {
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    if (pb.slab) { cudaFreeAsync(pb.slab, ctx->L.stream); pb.slab = nullptr; }
+    struct Recycle { arvc_ctx* c; PendingBatch& b; ~Recycle() { c->pinned_put(b.h_states, b.h_bytes); b.h_states = nullptr; } } recycle{ctx, pb};
+    if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
+    int err = 0;
+    for (int i = 0; i < pb.n_pairs; ++i) {
+        const PairState& st = pb.h_states[i];
+        err |= st.err;
+        if (!st.done) return ctx->fail(ARVC_E_CUDA, "icp: a pair did not terminate (internal error)");
+        if (rec) {
+            rec[i].pair = i; rec[i].updates = st.updates; rec[i].n_corr = st.ncorr; rec[i].passes = st.passes;
+            std::memcpy(rec[i].T, st.T, sizeof(double) * 16);
+            rec[i].fitness = st.fitness; rec[i].rmse = st.rmse;
+        }
+    }
+    if (err & ERR_HASH_FULL) return ctx->fail(ARVC_E_CAPACITY, "hash grid overflow in a scan of this batch");
+    if (err & ERR_VOXEL_RANGE) return ctx->fail(ARVC_E_CAPACITY, "voxel index outside the range implied by the filter bounds");
+    return ARVC_OK;
+}
+
+int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
+                         const arvc_icp_params* p, uint64_t* ticket) {
+    if (!ctx || !ticket) return ARVC_E_ARG;
+    PendingBatch pb;
+    const int rc = icp_enqueue(ctx, n_pairs, tgt_ids, src_ids, init_T, p, false, pb, nullptr, nullptr, nullptr);
+    if (rc) { if (pb.slab) cudaFreeAsync(pb.slab, ctx->L.stream); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    *ticket = ctx->next_ticket++;
+    ctx->pending[*ticket] = std::move(pb);
+    return ARVC_OK;
+}
+
+int arvc_icp_batch_finish(arvc_ctx* ctx, uint64_t ticket, arvc_result_record* records) {
+    if (!ctx) return ARVC_E_ARG;
+    auto it = ctx->pending.find(ticket);
+    if (it == ctx->pending.end()) return ctx->fail(ARVC_E_ARG, "icp_batch_finish: unknown ticket");
+    const int rc = icp_collect(ctx, it->second, records);
+    ctx->pending.erase(it);
+    return rc;
+}
+
+int arvc_icp_batch(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
+                   const arvc_icp_params* p, double* out_T, double* fitness, double* rmse, int32_t* updates, int32_t* n_corr) {
+    if (!ctx) return ARVC_E_ARG;
+    uint64_t ticket = 0;
+    int rc = arvc_icp_batch_async(ctx, n_pairs, tgt_ids, src_ids, init_T, p, &ticket);
+    if (rc) return rc;
+    std::vector<arvc_result_record> rec(std::max(n_pairs, 1));
+    rc = arvc_icp_batch_finish(ctx, ticket, rec.data());
+    if (rc) return rc;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (out_T) std::memcpy(out_T + 16 * (size_t)i, rec[i].T, sizeof(double) * 16);
+        if (fitness) fitness[i] = rec[i].fitness;
+        if (rmse) rmse[i] = rec[i].rmse;
+        if (updates) updates[i] = rec[i].updates;
+        if (n_corr) n_corr[i] = rec[i].n_corr;
+    }
+    return ARVC_OK;
+}
+
+int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* init_T, const arvc_icp_params* p, int32_t* corr,
+                   double* trace_T, double* trace_fitness, double* trace_rmse, int32_t* n_passes, arvc_result_record* result) {
+    if (!ctx) return ARVC_E_ARG;
+    PendingBatch pb;
+    int* d_ct = nullptr;
+    double* d_st = nullptr;
+    int cap = 0;
+    int rc = icp_enqueue(ctx, 1, &tgt_id, &src_id, init_T, p, true, pb, &d_ct, &d_st, &cap);
+    if (rc) { if (pb.slab) cudaFreeAsync(pb.slab, ctx->L.stream); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    const int passes_max = p->max_iter + 1;
+    std::vector<int> hct((size_t)cap * passes_max);
+    std::vector<double> hst((size_t)passes_max * 18);
+    CK(cudaMemcpyAsync(hct.data(), d_ct, sizeof(int) * hct.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(hst.data(), d_st, sizeof(double) * hst.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    arvc_result_record rec;
+    rc = icp_collect(ctx, pb, &rec);
+    if (rc) return rc;
+    Scan* s = ctx->find(src_id);
+    int c[CNT_WORDS];
+    rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    const int ns = c[CNT_NPTS];
+    for (int ps = 0; ps < rec.passes; ++ps) {
+        if (corr) std::memcpy(corr + (size_t)ps * ns, hct.data() + (size_t)ps * cap, sizeof(int) * ns);
+        if (trace_T) std::memcpy(trace_T + 16 * (size_t)ps, hst.data() + 18 * (size_t)ps, sizeof(double) * 16);
+        if (trace_fitness) trace_fitness[ps] = hst[18 * (size_t)ps + 16];
+        if (trace_rmse) trace_rmse[ps] = hst[18 * (size_t)ps + 17];
+    }
+    if (n_passes) *n_passes = rec.passes;
+    if (result) *result = rec;
+    return ARVC_OK;
+}
+
+void* arvc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void arvc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Host-side plumbing shared by the .cu files: launch helper, parameter blocks, stage entry points.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace arvc {
+
+struct FilterParams { double min_r2, max_r2, min_h, max_h; };
+struct VoxelParams { double voxel; int bx, by, bz, pad; };
+struct NormalParams { double radius; int max_nn; int level; };
+
+struct Launcher {
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    cudaError_t err = cudaSuccess;
+    template <typename... KArgs, typename... Args>
+    void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+        if (err != cudaSuccess) return;
+        if (grid.x == 0 || grid.y == 0) return;
+        kernel<<<grid, block, 0, stream>>>(args...);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) err = e;
+        ++launches;
+    }
+};
+
+// pair descriptor + state for the device-resident ICP iteration
+struct __align__(16) PairState {
+    double T[16];           // cumulative transformation used by the NEXT pass
+    double fitness, rmse;   // of the last completed pass
+    double sums[32];        // reduced normal-equation sums of the last pass (debug)
+    int passes;             // completed correspondence passes
+    int updates;            // executed updates
+    int done;
+    int ncorr;
+    unsigned ticket;
+    int err;                // OR of the two scans' device error flags
+    int pad[2];
+};
+
+struct PairDev {
+    const ScanDev* src;
+    const ScanDev* tgt;
+    PairState* state;
+    double* partials;       // [nblk][kSumStride]
+    int* prev;              // [src cap] Morton position of last pass' match in the target, or -1
+    int* corr_trace;        // optional [(max_iter+1)][src cap] (cloud order), may be null
+    double* state_trace;    // optional [(max_iter+1)][18]: T16, fitness, rmse
+};
+
+struct IcpParams {
+    double max_d2;          // max_corr_dist^2
+    double max_d;
+    double rel_fitness, rel_rmse;
+    int max_iter;
+    int method;
+};
+
+constexpr int kSumStride = 32;
+constexpr int kIcpBlock = 128;
+
+void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const FilterParams& fp, const VoxelParams& vp,
+                    bool voxel_on);
+void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow);
+void run_icp(Launcher& L, const PairDev* d_pairs, int n_pairs, int src_cap_max, const IcpParams& ip, int combos_mask);
+
+}  // namespace arvc

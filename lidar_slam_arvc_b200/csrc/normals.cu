@@ -1,0 +1,309 @@
+// Normal estimation: hybrid k-NN (k nearest, then d2 < r2) over the hash grid, per-point 3x3 covariance
+// and analytic smallest-eigenvector solve in registers.  One warp per point.
+//
+// Reference semantics restated: keyframemanager/keyframe.py:160-162
+//   pointcloud_filtered.estimate_normals(KDTreeSearchParamHybrid(radius=0.3, max_nn=300))
+// -> Open3D EstimatePerPointCovariances (SearchHybrid, ComputeCovariance) + ComputeNormal (FastEigen3x3).
+// Selection of the k nearest among more than k in-radius neighbours is exact: a monotone d2-histogram
+// finds the bucket holding the k-th neighbour, the bucket is ranked exactly by (d2, index).
+#include "engine.cuh"
+
+namespace arvc {
+
+namespace {
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 cross3(const V3& a, const V3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double dot3(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+struct Sym3 { double a00, a01, a02, a11, a12, a22; };
+
+__device__ V3 eigvec0(const Sym3& A, double ev) {
+    const V3 r0{A.a00 - ev, A.a01, A.a02}, r1{A.a01, A.a11 - ev, A.a12}, r2{A.a02, A.a12, A.a22 - ev};
+    const V3 c01 = cross3(r0, r1), c02 = cross3(r0, r2), c12 = cross3(r1, r2);
+    const double d0 = dot3(c01, c01), d1 = dot3(c02, c02), d2 = dot3(c12, c12);
+    double dmax = d0;
+    int imax = 0;
+    if (d1 > dmax) { dmax = d1; imax = 1; }
+    if (d2 > dmax) { imax = 2; }
+    const V3 c = imax == 0 ? c01 : (imax == 1 ? c02 : c12);
+    const double s = sqrt(imax == 0 ? d0 : (imax == 1 ? d1 : d2));
+    return {c.x / s, c.y / s, c.z / s};
+}
+
+__device__ V3 eigvec1(const Sym3& A, const V3& e0, double ev1) {
+    V3 U;
+    if (fabs(e0.x) > fabs(e0.y)) {
+        const double inv = 1.0 / sqrt(e0.x * e0.x + e0.z * e0.z);
+        U = {-e0.z * inv, 0.0, e0.x * inv};
+    } else {
+        const double inv = 1.0 / sqrt(e0.y * e0.y + e0.z * e0.z);
+        U = {0.0, e0.z * inv, -e0.y * inv};
+    }
+    const V3 V = cross3(e0, U);
+    const V3 AU{A.a00 * U.x + A.a01 * U.y + A.a02 * U.z, A.a01 * U.x + A.a11 * U.y + A.a12 * U.z, A.a02 * U.x + A.a12 * U.y + A.a22 * U.z};
+    const V3 AV{A.a00 * V.x + A.a01 * V.y + A.a02 * V.z, A.a01 * V.x + A.a11 * V.y + A.a12 * V.z, A.a02 * V.x + A.a12 * V.y + A.a22 * V.z};
+    double m00 = dot3(U, AU) - ev1, m01 = dot3(U, AV), m11 = dot3(V, AV) - ev1;
+    const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+    if (a00 >= a11) {
+        if (fmax(a00, a01) > 0) {
+            if (a00 >= a01) { m01 /= m00; m00 = 1 / sqrt(1 + m01 * m01); m01 *= m00; }
+            else            { m00 /= m01; m01 = 1 / sqrt(1 + m00 * m00); m00 *= m01; }
+            return {m01 * U.x - m00 * V.x, m01 * U.y - m00 * V.y, m01 * U.z - m00 * V.z};
+        }
+        return U;
+    }
+    if (fmax(a11, a01) > 0) {
+        if (a11 >= a01) { m01 /= m11; m11 = 1 / sqrt(1 + m01 * m01); m01 *= m11; }
+        else            { m11 /= m01; m01 = 1 / sqrt(1 + m11 * m11); m11 *= m01; }
+        return {m11 * U.x - m01 * V.x, m11 * U.y - m01 * V.y, m11 * U.z - m01 * V.z};
+    }
+    return U;
+}
+
+// covariance (symmetric, c00 c01 c02 c11 c12 c22) -> smallest-eigenvalue eigenvector, Open3D FastEigen3x3 scheme
+__device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, double c12, double c22) {
+    const double mx = fmax(fmax(fmax(c00, c01), fmax(c02, c11)), fmax(c12, c22));   // maxCoeff (not max-abs)
+    if (mx == 0) return {0, 0, 0};
+    const Sym3 A{c00 / mx, c01 / mx, c02 / mx, c11 / mx, c12 / mx, c22 / mx};
+    const double norm = A.a01 * A.a01 + A.a02 * A.a02 + A.a12 * A.a12;
+    if (norm > 0) {
+        const double q = (A.a00 + A.a11 + A.a22) / 3;
+        const double b00 = A.a00 - q, b11 = A.a11 - q, b22 = A.a22 - q;
+        const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
+        const double k00 = b11 * b22 - A.a12 * A.a12;
+        const double k01 = A.a01 * b22 - A.a12 * A.a02;
+        const double k02 = A.a01 * A.a12 - b11 * A.a02;
+        const double det = (b00 * k00 - A.a01 * k01 + A.a02 * k02) / (p * p * p);
+        double half_det = det * 0.5;
+        half_det = fmin(fmax(half_det, -1.0), 1.0);
+        const double angle = acos(half_det) / 3.0;
+        const double two_thirds_pi = 2.09439510239319549;
+        const double beta2 = cos(angle) * 2;
+        const double beta0 = cos(angle + two_thirds_pi) * 2;
+        const double beta1 = -(beta0 + beta2);
+        const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+        if (half_det >= 0) {
+            const V3 v2 = eigvec0(A, e2);
+            if (e2 < e0 && e2 < e1) return v2;
+            const V3 v1 = eigvec1(A, v2, e1);
+            if (e1 < e0 && e1 < e2) return v1;
+            return cross3(v1, v2);
+        }
+        const V3 v0 = eigvec0(A, e0);
+        if (e0 < e1 && e0 < e2) return v0;
+        const V3 v1 = eigvec1(A, v0, e1);
+        if (e1 < e0 && e1 < e2) return v1;
+        return cross3(v0, v1);
+    }
+    if (c00 < c11 && c00 < c22) return {1, 0, 0};
+    if (c11 < c00 && c11 < c22) return {0, 1, 0};
+    return {0, 0, 1};
+}
+
+constexpr int kNrmWarps = 8;
+constexpr int kBins = 512;
+constexpr int kCand = 128;
+
+__device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
+
+}  // namespace
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np) {
+    typedef typename RecT<WIDE>::type Rec;
+    __shared__ int s_hist[kNrmWarps][kBins];
+    __shared__ double s_cd2[kNrmWarps][kCand];
+    __shared__ int s_cidx[kNrmWarps][kCand];
+
+    const ScanDev& s = scans[blockIdx.y];
+    if ((s.wide != 0) != WIDE) return;
+    const int n = s.counts[CNT_NPTS];
+    const int w = threadIdx.x >> 5, lane = lane_id();
+    const int p = blockIdx.x * kNrmWarps + w;
+    if (p >= n) return;
+    const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(s.recs);
+    double qx, qy, qz;
+    int qidx;
+    load_rec(recs + p, qx, qy, qz, qidx);
+
+    const GridSpec g = s.grid;
+    const int L = np.level;
+    const double r2 = np.radius * np.radius;
+    const double rinf = np.radius * (1.0 + 1e-9) + 1e-12;
+    const double cl = g.c0 * (double)(1 << L);
+    const int x0 = cell_coord(qx - rinf, g.ox, g.inv_c0) >> L, x1 = cell_coord(qx + rinf, g.ox, g.inv_c0) >> L;
+    const int y0 = cell_coord(qy - rinf, g.oy, g.inv_c0) >> L, y1 = cell_coord(qy + rinf, g.oy, g.inv_c0) >> L;
+    const int z0 = cell_coord(qz - rinf, g.oz, g.inv_c0) >> L, z1 = cell_coord(qz + rinf, g.oz, g.inv_c0) >> L;
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+    const int ncell = nx * ny * nz;            // <= 27: the host picks the level with cell edge >= radius
+
+    int* hist = s_hist[w];
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    int cnt = 0;
+    double tau_d2 = r2;      // inclusion: d2 < r2 and (d2, idx) <= (tau_d2, tau_idx)
+    int tau_idx = 0x7fffffff;
+
+    // look the (<= 27) cells up once: lane c owns cell c; cells whose box misses the ball are skipped
+    unsigned st = 0, en = 0;
+    if (lane < ncell) {
+        const int cx = x0 + lane % nx, cy = y0 + (lane / nx) % ny, cz = z0 + lane / (nx * ny);
+        const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
+        const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cl)));
+        const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cl)));
+        const double ddz = fmax(0.0, fmax(bz0 - qz, qz - (bz0 + cl)));
+        if (ddx * ddx + ddy * ddy + ddz * ddz <= r2 * (1.0 + 1e-9) + 1e-12)
+            grid_lookup(s.table, s.table_mask, L, morton3(cx, cy, cz), st, en);
+    }
+    const int total = warp_sum((int)(en - st));
+    const bool need_select = total > np.max_nn;
+
+    int bstar = -1, need = 0;
+    const double bin_scale = (double)kBins / r2;
+    for (int phase = need_select ? 1 : 3; phase <= 3; ++phase) {
+        if (phase == 1) {
+            for (int b = lane; b < kBins; b += 32) hist[b] = 0;
+            __syncwarp();
+        }
+        int ncand = 0;
+        {
+            for (int cc = 0; cc < ncell; ++cc) {
+                const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+                for (unsigned t = cst; t < cen; t += 32) {
+                    const unsigned j = t + lane;
+                    double x = 0, y = 0, z = 0, d2 = INFINITY;
+                    int idx = 0;
+                    if (j < cen) {
+                        load_rec(recs + j, x, y, z, idx);
+                        d2 = sqdist(qx, qy, qz, x, y, z);
+                    }
+                    const bool in = d2 < r2;
+                    if (phase == 1) {
+                        if (in) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
+                    } else if (phase == 2) {
+                        const bool hit = in && min(kBins - 1, (int)(d2 * bin_scale)) == bstar;
+                        const unsigned m = __ballot_sync(kFull, hit);
+                        if (hit) {
+                            const int slot = ncand + __popc(m & ((1u << lane) - 1u));
+                            if (slot < kCand) { s_cd2[w][slot] = d2; s_cidx[w][slot] = idx; }
+                        }
+                        ncand += __popc(m);
+                    } else {
+                        if (in && !key_less(tau_d2, tau_idx, d2, idx)) {
+                            const double ux = x - qx, uy = y - qy, uz = z - qz;
+                            sx += ux; sy += uy; sz += uz;
+                            sxx += ux * ux; sxy += ux * uy; sxz += ux * uz; syy += uy * uy; syz += uy * uz; szz += uz * uz;
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+        if (phase == 1) {
+            __syncwarp();
+            // locate the bucket holding the max_nn-th neighbour: lane owns kBins/32 consecutive buckets
+            constexpr int per = kBins / 32;
+            int local = 0;
+#pragma unroll
+            for (int b = 0; b < per; ++b) local += hist[lane * per + b];
+            int inc = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int n_in = __shfl_sync(kFull, inc, 31);
+            if (n_in <= np.max_nn) { phase = 2; continue; }          // everything in radius is used: go to phase 3
+            int before = inc - local;
+            int myb = -1, myneed = 0;
+            if (before < np.max_nn && inc >= np.max_nn) {
+#pragma unroll
+                for (int b = 0; b < per; ++b) {
+                    const int h = hist[lane * per + b];
+                    if (myb < 0 && before + h >= np.max_nn) { myb = lane * per + b; myneed = np.max_nn - before; }
+                    before += h;
+                }
+            }
+            const unsigned who = __ballot_sync(kFull, myb >= 0);
+            const int src_lane = __ffs(who) - 1;
+            bstar = __shfl_sync(kFull, myb, src_lane);
+            need = __shfl_sync(kFull, myneed, src_lane);
+        } else if (phase == 2) {
+            __syncwarp();
+            if (ncand <= kCand) {
+                // exact rank inside the boundary bucket
+                double td2 = 0;
+                int tidx = 0;
+                bool have = false;
+                for (int a = lane; a < ncand; a += 32) {
+                    const double d2a = s_cd2[w][a];
+                    const int ia = s_cidx[w][a];
+                    int rank = 0;
+                    for (int b = 0; b < ncand; ++b) rank += key_less(s_cd2[w][b], s_cidx[w][b], d2a, ia) ? 1 : 0;
+                    if (rank == need - 1) { td2 = d2a; tidx = ia; have = true; }
+                }
+                const unsigned who = __ballot_sync(kFull, have);
+                const int src_lane = __ffs(who) - 1;
+                tau_d2 = __shfl_sync(kFull, td2, src_lane);
+                tau_idx = __shfl_sync(kFull, tidx, src_lane);
+            } else {
+                // pathological bucket (duplicates): extract the `need` smallest keys one at a time
+                double last_d2 = -1.0;
+                int last_idx = -1;
+                for (int t = 0; t < need; ++t) {
+                    double md2 = INFINITY;
+                    int midx = 0x7fffffff;
+                    {
+                        for (int cc = 0; cc < ncell; ++cc) {
+                            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+                            for (unsigned u = cst + lane; u < cen; u += 32) {
+                                double x, y, z;
+                                int idx;
+                                load_rec(recs + u, x, y, z, idx);
+                                const double d2 = sqdist(qx, qy, qz, x, y, z);
+                                if (d2 < r2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
+                                    key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od2 = __shfl_xor_sync(kFull, md2, o);
+                        const int oidx = __shfl_xor_sync(kFull, midx, o);
+                        if (key_less(od2, oidx, md2, midx)) { md2 = od2; midx = oidx; }
+                    }
+                    last_d2 = md2; last_idx = midx;
+                }
+                tau_d2 = last_d2; tau_idx = last_idx;
+            }
+        }
+    }
+
+    cnt = warp_sum(cnt);
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
+    syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
+    if (lane == 0) {
+        V3 nv;
+        if (cnt >= 3) {
+            const double inv = 1.0 / (double)cnt;
+            const double mx = sx * inv, my = sy * inv, mz = sz * inv;
+            nv = fast_eigen3x3(sxx * inv - mx * mx, sxy * inv - mx * my, sxz * inv - mx * mz, syy * inv - my * my, syz * inv - my * mz,
+                               szz * inv - mz * mz);
+        } else {
+            nv = fast_eigen3x3(1, 0, 0, 1, 0, 1);   // Open3D: covariance = Identity when fewer than 3 neighbours
+        }
+        if (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) == 0.0) nv = {0.0, 0.0, 1.0};
+        reinterpret_cast<double4*>(s.normals)[p] = make_double4(nv.x, nv.y, nv.z, 0.0);
+        s.nn_count[p] = cnt;
+    }
+}
+
+void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow) {
+    if (n_scans == 0 || cap_max == 0) return;
+    const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
+    if (any_narrow) L.launch(k_normals<false>, grid, block, d_scans, np);
+    if (any_wide) L.launch(k_normals<true>, grid, block, d_scans, np);
+}
+
+}  // namespace arvc

@@ -1,0 +1,247 @@
+"""ctypes binding of libarvc_icp.so (C-ABI in include/arvc_icp.h).
+
+This is the only module that talks to the native library.  There is no CPU fallback: if the library is
+missing or no CUDA device is present, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarvc_icp.so")
+
+P2P, P2PLANE = 0, 1
+
+# every symbol include/arvc_icp.h declares (checked by tests/test_abi.py without a GPU)
+EXPORTED_SYMBOLS = [
+    "arvc_ctx_create", "arvc_ctx_destroy", "arvc_last_error", "arvc_sync", "arvc_stream", "arvc_version",
+    "arvc_kernel_launches", "arvc_scan_upload_f32", "arvc_scan_upload_f64", "arvc_scan_free", "arvc_scan_preprocess",
+    "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
+    "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
+    "arvc_host_alloc", "arvc_host_free",
+]
+
+
+class PreprocessParams(ctypes.Structure):
+    _fields_ = [("min_radius2", ctypes.c_double), ("max_radius2", ctypes.c_double), ("min_height", ctypes.c_double),
+                ("max_height", ctypes.c_double), ("voxel_size", ctypes.c_double), ("normal_radius", ctypes.c_double),
+                ("max_nn", ctypes.c_int32), ("want_normals", ctypes.c_int32), ("grid_cell", ctypes.c_double),
+                ("grid_max_dist", ctypes.c_double)]
+
+
+class IcpParams(ctypes.Structure):
+    _fields_ = [("max_corr_dist", ctypes.c_double), ("rel_fitness", ctypes.c_double), ("rel_rmse", ctypes.c_double),
+                ("max_iter", ctypes.c_int32), ("method", ctypes.c_int32)]
+
+
+class ResultRecord(ctypes.Structure):
+    _fields_ = [("pair", ctypes.c_int32), ("updates", ctypes.c_int32), ("n_corr", ctypes.c_int32), ("passes", ctypes.c_int32),
+                ("T", ctypes.c_double * 16), ("fitness", ctypes.c_double), ("rmse", ctypes.c_double)]
+
+
+RESULT_DTYPE = np.dtype([("pair", "<i4"), ("updates", "<i4"), ("n_corr", "<i4"), ("passes", "<i4"), ("T", "<f8", (4, 4)),
+                         ("fitness", "<f8"), ("rmse", "<f8")])
+assert RESULT_DTYPE.itemsize == ctypes.sizeof(ResultRecord) == 160
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine.  Raises (loudly) when it has not been built: `python -c 'import __graft_entry__ as g; g.build()'`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("native CUDA library %s is missing; build it with __graft_entry__.build() "
+                           "(make -C lidar_slam_arvc_b200/csrc). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i64p, dp, ip, fp = c.c_void_p, c.POINTER(c.c_int64), c.POINTER(c.c_double), c.POINTER(c.c_int32), c.POINTER(c.c_float)
+    lib.arvc_ctx_create.argtypes = [c.c_int, c.POINTER(vp)]
+    lib.arvc_ctx_destroy.argtypes = [vp]
+    lib.arvc_ctx_destroy.restype = None
+    lib.arvc_last_error.argtypes = [vp]
+    lib.arvc_last_error.restype = c.c_char_p
+    lib.arvc_sync.argtypes = [vp]
+    lib.arvc_stream.argtypes = [vp]
+    lib.arvc_stream.restype = vp
+    lib.arvc_kernel_launches.argtypes = [vp]
+    lib.arvc_kernel_launches.restype = c.c_int64
+    lib.arvc_scan_upload_f32.argtypes = [vp, c.c_int64, vp, c.c_int]
+    lib.arvc_scan_upload_f64.argtypes = [vp, c.c_int64, vp, c.c_int]
+    lib.arvc_scan_free.argtypes = [vp, c.c_int64]
+    lib.arvc_scan_preprocess.argtypes = [vp, c.c_int, i64p, c.POINTER(PreprocessParams)]
+    lib.arvc_scan_info.argtypes = [vp, c.c_int64, ip, ip, ip, ip]
+    lib.arvc_scan_get_points.argtypes = [vp, c.c_int64, dp, dp]
+    lib.arvc_scan_get_filter_indices.argtypes = [vp, c.c_int64, ip]
+    lib.arvc_scan_get_voxels.argtypes = [vp, c.c_int64, ip, ip]
+    lib.arvc_scan_get_nn_counts.argtypes = [vp, c.c_int64, ip]
+    lib.arvc_icp_batch.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), dp, dp, dp, ip, ip]
+    lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
+    lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
+    lib.arvc_icp_trace.argtypes = [vp, c.c_int64, c.c_int64, dp, c.POINTER(IcpParams), ip, dp, dp, dp, ip, c.POINTER(ResultRecord)]
+    lib.arvc_host_alloc.argtypes = [c.c_size_t]
+    lib.arvc_host_alloc.restype = vp
+    lib.arvc_host_free.argtypes = [vp]
+    lib.arvc_host_free.restype = None
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _i64p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One context = one GPU + one stream.  Not thread-safe (calls are serialised by the caller, like the reference)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.arvc_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError("arvc_ctx_create failed (%d): %s" % (rc, self.lib.arvc_last_error(None).decode()))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.arvc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError("engine error %d: %s" % (rc, self.lib.arvc_last_error(self.h).decode()))
+
+    # ---- scans
+    def upload(self, scan_id, xyz):
+        """xyz: [n,3] float32 (PCD payload) or float64.  A pinned buffer must stay alive until sync()."""
+        a = np.asarray(xyz)
+        if a.dtype == np.float64:
+            a = np.ascontiguousarray(a)
+            self._ck(self.lib.arvc_scan_upload_f64(self.h, int(scan_id), a.ctypes.data, len(a)))
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            self._ck(self.lib.arvc_scan_upload_f32(self.h, int(scan_id), a.ctypes.data, len(a)))
+        return a
+
+    def upload_ptr(self, scan_id, ptr, n):
+        self._ck(self.lib.arvc_scan_upload_f32(self.h, int(scan_id), ctypes.c_void_p(ptr), int(n)))
+
+    def free(self, scan_id):
+        self._ck(self.lib.arvc_scan_free(self.h, int(scan_id)))
+
+    @staticmethod
+    def make_preprocess_params(min_radius=0.5, max_radius=35, min_height=-1.0, max_height=50.0, voxel_size=None,
+                               normal_radius=0.3, max_nn=300, want_normals=True, grid_cell=0.0, grid_max_dist=10.0):
+        # `radius ** 2` evaluated by Python exactly as keyframe.py:92 does
+        return PreprocessParams(float(min_radius ** 2), float(max_radius ** 2), float(min_height), float(max_height),
+                                float("nan") if voxel_size is None else float(voxel_size), float(normal_radius), int(max_nn),
+                                1 if want_normals else 0, float(grid_cell), float(grid_max_dist))
+
+    def preprocess(self, scan_ids, params):
+        ids = np.ascontiguousarray(scan_ids, dtype=np.int64).reshape(-1)
+        self._ck(self.lib.arvc_scan_preprocess(self.h, len(ids), _i64p(ids), ctypes.byref(params)))
+
+    def info(self, scan_id):
+        v = [ctypes.c_int32() for _ in range(4)]
+        self._ck(self.lib.arvc_scan_info(self.h, int(scan_id), *[ctypes.byref(x) for x in v]))
+        return {"n_raw": v[0].value, "n_filtered": v[1].value, "n_points": v[2].value, "has_normals": bool(v[3].value)}
+
+    def get_points(self, scan_id, normals=False):
+        n = self.info(scan_id)["n_points"]
+        xyz = np.empty((n, 3))
+        nrm = np.empty((n, 3)) if normals else None
+        self._ck(self.lib.arvc_scan_get_points(self.h, int(scan_id), _dp(xyz), _dp(nrm) if normals else None))
+        return (xyz, nrm) if normals else xyz
+
+    def get_filter_indices(self, scan_id):
+        n = self.info(scan_id)["n_filtered"]
+        idx = np.empty(max(n, 1), dtype=np.int32)
+        self._ck(self.lib.arvc_scan_get_filter_indices(self.h, int(scan_id), _ip(idx)))
+        return idx[:n]
+
+    def get_voxels(self, scan_id):
+        n = self.info(scan_id)["n_points"]
+        keys = np.empty((max(n, 1), 3), dtype=np.int32)
+        cnt = np.empty(max(n, 1), dtype=np.int32)
+        self._ck(self.lib.arvc_scan_get_voxels(self.h, int(scan_id), _ip(keys), _ip(cnt)))
+        return keys[:n], cnt[:n]
+
+    def get_nn_counts(self, scan_id):
+        n = self.info(scan_id)["n_points"]
+        cnt = np.empty(max(n, 1), dtype=np.int32)
+        self._ck(self.lib.arvc_scan_get_nn_counts(self.h, int(scan_id), _ip(cnt)))
+        return cnt[:n]
+
+    # ---- registration
+    @staticmethod
+    def make_icp_params(method=P2PLANE, max_corr_dist=10.0, rel_fitness=1e-6, rel_rmse=1e-6, max_iter=30):
+        return IcpParams(float(max_corr_dist), float(rel_fitness), float(rel_rmse), int(max_iter), int(method))
+
+    def icp_batch_async(self, tgt_ids, src_ids, init_T, params):
+        t = np.ascontiguousarray(tgt_ids, dtype=np.int64).reshape(-1)
+        s = np.ascontiguousarray(src_ids, dtype=np.int64).reshape(-1)
+        T = np.ascontiguousarray(init_T, dtype=np.float64).reshape(-1, 16)
+        assert len(t) == len(s) == len(T)
+        ticket = ctypes.c_uint64()
+        self._ck(self.lib.arvc_icp_batch_async(self.h, len(t), _i64p(t), _i64p(s), _dp(T), ctypes.byref(params), ctypes.byref(ticket)))
+        return ticket.value, len(t)
+
+    def icp_batch_finish(self, ticket):
+        tk, n = ticket
+        rec = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
+        self._ck(self.lib.arvc_icp_batch_finish(self.h, ctypes.c_uint64(tk), rec.ctypes.data))
+        return rec[:n]
+
+    def icp_batch(self, tgt_ids, src_ids, init_T, params):
+        """Returns a structured array (RESULT_DTYPE): T[4,4], fitness, rmse, updates, n_corr, passes per pair."""
+        return self.icp_batch_finish(self.icp_batch_async(tgt_ids, src_ids, init_T, params))
+
+    def icp_trace(self, tgt_id, src_id, init_T, params):
+        ns = self.info(src_id)["n_points"]
+        passes = params.max_iter + 1
+        corr = np.full((passes, max(ns, 1)), -2, dtype=np.int32)
+        trT = np.zeros((passes, 4, 4))
+        trf = np.zeros(passes)
+        trr = np.zeros(passes)
+        npass = ctypes.c_int32()
+        rec = ResultRecord()
+        T = np.ascontiguousarray(init_T, dtype=np.float64).reshape(16)
+        # the C side packs rows with stride n_src
+        flat = np.full(passes * max(ns, 1), -2, dtype=np.int32)
+        self._ck(self.lib.arvc_icp_trace(self.h, int(tgt_id), int(src_id), _dp(T), ctypes.byref(params), _ip(flat), _dp(trT),
+                                         _dp(trf), _dp(trr), ctypes.byref(npass), ctypes.byref(rec)))
+        k = npass.value
+        corr = flat[:k * ns].reshape(k, ns) if ns > 0 else np.zeros((k, 0), dtype=np.int32)
+        out = np.zeros(1, dtype=RESULT_DTYPE)
+        ctypes.memmove(out.ctypes.data, ctypes.byref(rec), 160)
+        return {"corr": corr, "T": trT[:k], "fitness": trf[:k], "rmse": trr[:k], "passes": k, "result": out[0]}
+
+    def sync(self):
+        self._ck(self.lib.arvc_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.arvc_kernel_launches(self.h))
+
+    def stream_handle(self):
+        return self.lib.arvc_stream(self.h)

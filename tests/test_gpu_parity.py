@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs.  Bar (BASELINE.json north_star): filter / voxel keys / correspondence indices bit-exact; final
+transforms within 1e-4 rad and 1e-4 m; fitness and RMSE within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from lidar_slam_arvc_b200 import engine, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-4          # metres / radians (north_star)
+TOL_REL = 1e-5        # fitness, rmse relative (north_star)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def seq16():
+    return synth.Sequence(4, synth.TINY_16, start=30.0)
+
+
+@pytest.fixture(scope="module")
+def seq32():
+    return synth.Sequence(3, synth.SMALL_32, start=12.0)
+
+
+def rot_angle(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return float(np.arccos(np.clip(c, -1, 1)))
+
+
+def assert_transform_close(Tg, To):
+    assert np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < TOL_T
+    assert rot_angle(Tg[:3, :3], To[:3, :3]) < TOL_T
+    np.testing.assert_array_equal(Tg[3], [0, 0, 0, 1])
+
+
+def assert_rel(a, b):
+    assert abs(a - b) <= TOL_REL * max(abs(b), 1e-300), (a, b)
+
+
+# ------------------------------------------------------------------------------------------ filter
+def test_filter_bit_exact_golden(eng, golden_dir):
+    g = np.load(os.path.join(golden_dir, "filter_radius_height.npz"))
+    pts = g["points_f32"]
+    eng.upload(900, pts)
+    eng.preprocess([900], eng.make_preprocess_params(want_normals=False))
+    idx = eng.get_filter_indices(900)
+    np.testing.assert_array_equal(pts[idx].astype(np.float64), g["kept_default"])
+    np.testing.assert_array_equal(eng.get_points(900), g["kept_default"])       # cloud order = filter order
+    r, h = g["custom_radii"], g["custom_heights"]
+    eng.preprocess([900], eng.make_preprocess_params(r[0], r[1], h[0], h[1], want_normals=False))
+    np.testing.assert_array_equal(eng.get_points(900), g["kept_custom"])
+    eng.free(900)
+
+
+def test_filter_and_info_on_scan(eng, seq32):
+    s = seq32.scans[0]
+    eng.upload(1, s)
+    eng.preprocess([1], eng.make_preprocess_params(want_normals=False))
+    keep = orc.filter_radius_height(s.astype(np.float64))
+    np.testing.assert_array_equal(eng.get_filter_indices(1), keep)
+    info = eng.info(1)
+    assert info == {"n_raw": len(s), "n_filtered": len(keep), "n_points": len(keep), "has_normals": False}
+    # float64 upload path gives the same cloud
+    eng.upload(2, s.astype(np.float64))
+    eng.preprocess([2], eng.make_preprocess_params(want_normals=False))
+    np.testing.assert_array_equal(eng.get_points(2), eng.get_points(1))
+    eng.free(1)
+    eng.free(2)
+
+
+# ------------------------------------------------------------------------------------------ voxel
+@pytest.mark.parametrize("voxel", [0.2, 0.5, 0.05])
+def test_voxel_keys_and_means(eng, seq32, voxel):
+    s = seq32.scans[1]
+    eng.upload(3, s)
+    eng.preprocess([3], eng.make_preprocess_params(voxel_size=voxel, want_normals=False))
+    p = s.astype(np.float64)
+    p = p[orc.filter_radius_height(p)]
+    out, keys, cnt = orc.voxel_down_sample(p, voxel)
+    gk, gc = eng.get_voxels(3)
+    np.testing.assert_array_equal(gk, keys)            # integer voxel keys bit-exact, same (key-sorted) order
+    np.testing.assert_array_equal(gc, cnt)
+    np.testing.assert_array_equal(eng.get_points(3), out)   # means: same summation order -> bit-exact
+    eng.free(3)
+
+
+# ------------------------------------------------------------------------------------------ normals
+@pytest.mark.parametrize("max_nn,radius", [(300, 0.3), (20, 0.3), (5, 1.0)])
+def test_normals_vs_oracle(eng, seq32, max_nn, radius):
+    s = seq32.scans[0]
+    eng.upload(4, s)
+    eng.preprocess([4], eng.make_preprocess_params(normal_radius=radius, max_nn=max_nn))
+    pts, nrm = eng.get_points(4, normals=True)
+    on, cov, cnt = orc.estimate_normals(pts, radius, max_nn, return_cov=True)
+    np.testing.assert_array_equal(eng.get_nn_counts(4), cnt)          # same neighbour count after k / radius cut
+    assert (cnt == max_nn).any()
+    # same formulas in float64 on both sides: identical up to summation order except where the two smallest
+    # eigenvalues (nearly) coincide and the eigenvector is ill-conditioned
+    w = np.linalg.eigvalsh(cov)
+    gap = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300)
+    err = np.linalg.norm(nrm - on, axis=1)
+    assert (np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-9).all()
+    assert (err[gap > 1e-6] < 1e-6).all()
+    assert (err < 1e-6).mean() > 0.999
+    few = cnt < 3
+    np.testing.assert_array_equal(nrm[few], np.tile([0.0, 0.0, 1.0], (few.sum(), 1)))
+    eng.free(4)
+
+
+def test_normals_duplicates_and_tiny_clouds(eng):
+    # many exact duplicates stress the k-th-distance tie path (lowest index wins) and the pathological bucket path
+    rng = np.random.default_rng(0)
+    base = rng.uniform(1.0, 1.6, size=(40, 3)).astype(np.float32)
+    pts = np.vstack([base] * 12 + [np.array([[5.0, 5.0, 1.0], [5.0, 5.1, 1.0]], dtype=np.float32)])
+    eng.upload(5, pts)
+    eng.preprocess([5], eng.make_preprocess_params(normal_radius=0.3, max_nn=25))
+    gp, gn = eng.get_points(5, normals=True)
+    on, cov, cnt = orc.estimate_normals(gp, 0.3, 25, return_cov=True)
+    np.testing.assert_array_equal(eng.get_nn_counts(5), cnt)
+    w = np.linalg.eigvalsh(cov)
+    ok = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300) > 1e-6
+    assert (np.linalg.norm(gn - on, axis=1)[ok] < 1e-6).all()
+    np.testing.assert_array_equal(gn[-2:], [[0, 0, 1], [0, 0, 1]])
+    eng.free(5)
+
+
+# ------------------------------------------------------------------------------------------ ICP
+def _run_pair(eng, seq, i, j, method, voxel=None, f64=False, init=None, **icp_kw):
+    want_n = method == engine.P2PLANE
+    for k in (i, j):
+        eng.upload(k, seq.scans[k].astype(np.float64) if f64 else seq.scans[k])
+    pp = eng.make_preprocess_params(voxel_size=voxel, want_normals=want_n)
+    eng.preprocess([i, j], pp)
+    init = seq.relative_odo(i, j) if init is None else init
+    ip = eng.make_icp_params(method, **icp_kw)
+    tr = eng.icp_trace(i, j, init, ip)
+    tgt, tn = (eng.get_points(i, normals=True) if want_n else (eng.get_points(i), None))
+    src = eng.get_points(j)
+    # the device clouds ARE the oracle's clouds
+    otgt, _ = orc.preprocess(seq.scans[i], voxel_size=voxel, method="icppointpoint")
+    np.testing.assert_array_equal(tgt, otgt)
+    on = orc.estimate_normals(otgt) if want_n else None
+    osrc, _ = orc.preprocess(seq.scans[j], voxel_size=voxel, method="icppointpoint")
+    ref = orc.icp(osrc, otgt, on, init, orc.P2PLANE if want_n else orc.P2P, **icp_kw)
+    return tr, ref, src, tgt, tn
+
+
+@pytest.mark.parametrize("method", [engine.P2PLANE, engine.P2P])
+def test_icp_correspondences_exact_and_result(eng, seq16, method):
+    tr, ref, src, tgt, _ = _run_pair(eng, seq16, 0, 1, method)
+    # every pass: correspondence indices bit-exact against the oracle evaluated at the same transformation
+    for k in range(tr["passes"]):
+        corr, d2, fit, rmse = orc.correspondences(src, tgt, tr["T"][k], 10.0)
+        np.testing.assert_array_equal(tr["corr"][k], corr)
+        assert tr["fitness"][k] == fit
+        assert_rel(tr["rmse"][k], rmse)
+    res = tr["result"]
+    assert res["passes"] == ref.passes and res["updates"] == ref.updates
+    assert_transform_close(res["T"], ref.transformation)
+    assert_rel(res["fitness"], ref.fitness)
+    assert_rel(res["rmse"], ref.inlier_rmse)
+    assert res["n_corr"] == ref.n_corr
+    # and the whole trajectory of the iteration matches the oracle's
+    np.testing.assert_allclose(tr["T"], ref.trace_T, atol=1e-9)
+    np.testing.assert_allclose(tr["rmse"], ref.trace_rmse, rtol=1e-9)
+
+
+@pytest.mark.parametrize("method", [engine.P2PLANE, engine.P2P])
+def test_icp_small_cutoff_and_bad_init(eng, seq16, method):
+    # a 0.5 m cut-off leaves many source points without correspondence; the init is 0.4 m / 3 deg off
+    init = seq16.relative_gt(1, 2) @ synth.pose_matrix(0.3, -0.25, 0.05, np.deg2rad(3.0), 0.01, -0.01)
+    tr, ref, src, tgt, _ = _run_pair(eng, seq16, 1, 2, method, init=init, max_corr_dist=0.5)
+    assert 0 < tr["result"]["n_corr"] < len(src)
+    for k in range(tr["passes"]):
+        corr, _, fit, _ = orc.correspondences(src, tgt, tr["T"][k], 0.5)
+        np.testing.assert_array_equal(tr["corr"][k], corr)
+        assert tr["fitness"][k] == fit
+    assert tr["result"]["passes"] == ref.passes
+    assert_transform_close(tr["result"]["T"], ref.transformation)
+    assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
+
+
+@pytest.mark.parametrize("method,voxel,f64", [(engine.P2PLANE, 0.2, False), (engine.P2P, 0.3, False), (engine.P2PLANE, None, True)])
+def test_icp_wide_records(eng, seq32, method, voxel, f64):
+    tr, ref, src, tgt, _ = _run_pair(eng, seq32, 0, 1, method, voxel=voxel, f64=f64)
+    for k in (0, tr["passes"] - 1):
+        corr, _, fit, _ = orc.correspondences(src, tgt, tr["T"][k], 10.0)
+        np.testing.assert_array_equal(tr["corr"][k], corr)
+    assert tr["result"]["passes"] == ref.passes
+    assert_transform_close(tr["result"]["T"], ref.transformation)
+    assert_rel(tr["result"]["fitness"], ref.fitness)
+    assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
+
+
+def test_icp_batch_matches_single_and_is_deterministic(eng, seq16):
+    for k in range(4):
+        eng.upload(k, seq16.scans[k])
+    eng.preprocess([0, 1, 2, 3], eng.make_preprocess_params())
+    ip = eng.make_icp_params(engine.P2PLANE)
+    tg, sr = [0, 1, 2, 0, 3], [1, 2, 3, 2, 0]
+    init = np.array([seq16.relative_odo(a, b) for a, b in zip(tg, sr)])
+    r1 = eng.icp_batch(tg, sr, init, ip)
+    r2 = eng.icp_batch(tg, sr, init, ip)
+    np.testing.assert_array_equal(r1["T"], r2["T"])                     # bit-reproducible run to run
+    for k, (a, b) in enumerate(zip(tg, sr)):
+        single = eng.icp_batch([a], [b], init[k:k + 1], ip)[0]
+        np.testing.assert_array_equal(single["T"], r1["T"][k])
+        tgt, tn = eng.get_points(a, normals=True)
+        ref = orc.icp(eng.get_points(b), tgt, orc.estimate_normals(tgt), init[k], orc.P2PLANE)
+        assert r1["updates"][k] == ref.updates
+        assert_transform_close(r1["T"][k], ref.transformation)
+        assert_rel(r1["rmse"][k], ref.inlier_rmse)
+
+
+def test_icp_edge_cases(eng, seq16):
+    for k in range(2):
+        eng.upload(k, seq16.scans[k])
+    eng.upload(7, np.zeros((0, 3), dtype=np.float32))                            # empty scan
+    eng.upload(8, np.full((50, 3), 1000.0, dtype=np.float32))                    # everything filtered out
+    eng.preprocess([0, 1, 7, 8], eng.make_preprocess_params())
+    assert eng.info(7)["n_points"] == 0 and eng.info(8)["n_points"] == 0
+    ip = eng.make_icp_params(engine.P2PLANE, max_corr_dist=1.0)
+    far = np.eye(4)
+    far[:3, 3] = (500.0, 0, 0)
+    r = eng.icp_batch([0, 0, 0], [1, 7, 8], np.array([far, np.eye(4), np.eye(4)]), ip)
+    # nothing within the cut-off: fitness = rmse = 0 and the transformation is the init (Open3D returns identity updates)
+    assert r["fitness"][0] == 0 and r["rmse"][0] == 0 and r["n_corr"][0] == 0 and r["passes"][0] == 2
+    np.testing.assert_array_equal(r["T"][0], far)
+    assert (r["fitness"][1:] == 0).all() and (r["n_corr"][1:] == 0).all()
+    # max_iter = 0: evaluation only
+    r0 = eng.icp_batch([0], [1], seq16.relative_odo(0, 1)[None], eng.make_icp_params(engine.P2PLANE, max_iter=0))[0]
+    assert r0["passes"] == 1 and r0["updates"] == 0
+    np.testing.assert_array_equal(r0["T"], seq16.relative_odo(0, 1))
+    # empty target
+    r1 = eng.icp_batch([7], [1], np.eye(4)[None], ip)[0]
+    assert r1["fitness"] == 0 and r1["n_corr"] == 0
+
+
+def test_error_behaviour(eng, seq16):
+    eng.upload(0, seq16.scans[0])
+    eng.upload(1, seq16.scans[1])
+    eng.preprocess([0, 1], eng.make_preprocess_params(want_normals=False))
+    with pytest.raises(engine.EngineError, match="normals"):
+        eng.icp_batch([0], [1], np.eye(4)[None], eng.make_icp_params(engine.P2PLANE))
+    with pytest.raises(engine.EngineError, match="not uploaded"):
+        eng.icp_batch([0], [12345], np.eye(4)[None], eng.make_icp_params(engine.P2P))
+    with pytest.raises(engine.EngineError, match="unknown method"):
+        eng.icp_batch([0], [1], np.eye(4)[None], eng.make_icp_params(7))
+    with pytest.raises(engine.EngineError, match="unknown scan"):
+        eng.preprocess([777], eng.make_preprocess_params())
+    eng.free(0)
+    with pytest.raises(engine.EngineError):
+        eng.icp_batch([0], [1], np.eye(4)[None], eng.make_icp_params(engine.P2P))
+
+
+def test_full_size_64_beam_pair(eng):
+    """BASELINE config 2 shape: one OS1-64 pair, point-to-plane, against the oracle."""
+    seq = synth.Sequence(2, synth.OS1_64, start=30.0)
+    tr, ref, src, tgt, tn = _run_pair(eng, seq, 0, 1, engine.P2PLANE)
+    for k in (0, 1, tr["passes"] - 1):
+        corr, _, fit, rmse = orc.correspondences(src, tgt, tr["T"][k], 10.0)
+        np.testing.assert_array_equal(tr["corr"][k], corr)
+        assert tr["fitness"][k] == fit
+    on, cov, cnt = orc.estimate_normals(tgt, return_cov=True)
+    np.testing.assert_array_equal(eng.get_nn_counts(0), cnt)
+    assert (np.linalg.norm(tn - on, axis=1) < 1e-6).mean() > 0.999
+    assert tr["result"]["passes"] == ref.passes
+    assert_transform_close(tr["result"]["T"], ref.transformation)
+    assert_rel(tr["result"]["fitness"], ref.fitness)
+    assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
