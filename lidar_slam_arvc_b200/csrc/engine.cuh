@@ -18,9 +18,13 @@ struct Launcher {
     cudaError_t err = cudaSuccess;
     template <typename... KArgs, typename... Args>
     void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+        launch_smem(kernel, grid, block, 0, args...);
+    }
+    template <typename... KArgs, typename... Args>
+    void launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
         if (err != cudaSuccess) return;
         if (grid.x == 0 || grid.y == 0) return;
-        kernel<<<grid, block, 0, stream>>>(args...);
+        kernel<<<grid, block, smem, stream>>>(args...);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) err = e;
         ++launches;

@@ -62,8 +62,9 @@ __device__ V3 eigvec1(const Sym3& A, const V3& e0, double ev1) {
 }
 
 // covariance (symmetric, c00 c01 c02 c11 c12 c22) -> smallest-eigenvalue eigenvector, Open3D FastEigen3x3 scheme
-__device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, double c12, double c22) {
+__device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, double c12, double c22, double* rel_gap) {
     const double mx = fmax(fmax(fmax(c00, c01), fmax(c02, c11)), fmax(c12, c22));   // maxCoeff (not max-abs)
+    *rel_gap = 0.0;
     if (mx == 0) return {0, 0, 0};
     const Sym3 A{c00 / mx, c01 / mx, c02 / mx, c11 / mx, c12 / mx, c22 / mx};
     const double norm = A.a01 * A.a01 + A.a02 * A.a02 + A.a12 * A.a12;
@@ -83,6 +84,7 @@ __device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, doub
         const double beta0 = cos(angle + two_thirds_pi) * 2;
         const double beta1 = -(beta0 + beta2);
         const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+        *rel_gap = (e1 - e0) / fmax(fmax(fabs(e0), fabs(e2)), 1e-300);
         if (half_det >= 0) {
             const V3 v2 = eigvec0(A, e2);
             if (e2 < e0 && e2 < e1) return v2;
@@ -96,6 +98,10 @@ __device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, doub
         if (e1 < e0 && e1 < e2) return v1;
         return cross3(v0, v1);
     }
+    {
+        const double lo = fmin(c00, fmin(c11, c22)), hi = fmax(c00, fmax(c11, c22)), mid = c00 + c11 + c22 - lo - hi;
+        *rel_gap = (mid - lo) / fmax(fmax(fabs(lo), fabs(hi)), 1e-300);
+    }
     if (c00 < c11 && c00 < c22) return {1, 0, 0};
     if (c11 < c00 && c11 < c22) return {0, 1, 0};
     return {0, 0, 1};
@@ -104,6 +110,13 @@ __device__ V3 fast_eigen3x3(double c00, double c01, double c02, double c11, doub
 constexpr int kNrmWarps = 8;
 constexpr int kBins = 512;
 constexpr int kCand = 128;
+constexpr int kCanon = 320;          // most neighbours the canonical (sorted, sequential) re-summation handles
+// per-warp shared memory, two layouts that are never live at the same time:
+//   selection : int hist[kBins] | double cand_d2[kCand] | int cand_idx[kCand]
+//   canonical : double key_d2[kCanon] | int key_idx[kCanon] | int key_pos[kCanon] | int order[kCanon]
+constexpr int kWarpSmem = kCanon * 20;
+static_assert(kBins * 4 + kCand * 12 <= kWarpSmem, "selection layout must fit");
+constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
 
 __device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
@@ -112,10 +125,7 @@ __device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib)
 template <bool WIDE>
 __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np) {
     typedef typename RecT<WIDE>::type Rec;
-    __shared__ int s_hist[kNrmWarps][kBins];
-    __shared__ double s_cd2[kNrmWarps][kCand];
-    __shared__ int s_cidx[kNrmWarps][kCand];
-
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const ScanDev& s = scans[blockIdx.y];
     if ((s.wide != 0) != WIDE) return;
     const int n = s.counts[CNT_NPTS];
@@ -138,7 +148,10 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
     const int ncell = nx * ny * nz;            // <= 27: the host picks the level with cell edge >= radius
 
-    int* hist = s_hist[w];
+    unsigned char* wmem = s_raw + (size_t)w * kWarpSmem;
+    int* hist = reinterpret_cast<int*>(wmem);
+    double* cand_d2 = reinterpret_cast<double*>(wmem + kBins * 4);
+    int* cand_idx = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 8);
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
     int cnt = 0;
     double tau_d2 = r2;      // inclusion: d2 < r2 and (d2, idx) <= (tau_d2, tau_idx)
@@ -185,14 +198,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
                         const unsigned m = __ballot_sync(kFull, hit);
                         if (hit) {
                             const int slot = ncand + __popc(m & ((1u << lane) - 1u));
-                            if (slot < kCand) { s_cd2[w][slot] = d2; s_cidx[w][slot] = idx; }
+                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = idx; }
                         }
                         ncand += __popc(m);
                     } else {
                         if (in && !key_less(tau_d2, tau_idx, d2, idx)) {
                             const double ux = x - qx, uy = y - qy, uz = z - qz;
                             sx += ux; sy += uy; sz += uz;
-                            sxx += ux * ux; sxy += ux * uy; sxz += ux * uz; syy += uy * uy; syz += uy * uz; szz += uz * uz;
+                            sxx = fma(ux, ux, sxx); sxy = fma(ux, uy, sxy); sxz = fma(ux, uz, sxz);
+                            syy = fma(uy, uy, syy); syz = fma(uy, uz, syz); szz = fma(uz, uz, szz);
                             ++cnt;
                         }
                     }
@@ -236,10 +250,10 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
                 int tidx = 0;
                 bool have = false;
                 for (int a = lane; a < ncand; a += 32) {
-                    const double d2a = s_cd2[w][a];
-                    const int ia = s_cidx[w][a];
+                    const double d2a = cand_d2[a];
+                    const int ia = cand_idx[a];
                     int rank = 0;
-                    for (int b = 0; b < ncand; ++b) rank += key_less(s_cd2[w][b], s_cidx[w][b], d2a, ia) ? 1 : 0;
+                    for (int b = 0; b < ncand; ++b) rank += key_less(cand_d2[b], cand_idx[b], d2a, ia) ? 1 : 0;
                     if (rank == need - 1) { td2 = d2a; tidx = ia; have = true; }
                 }
                 const unsigned who = __ballot_sync(kFull, have);
@@ -283,16 +297,79 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
     syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
+    V3 nv{0.0, 0.0, 1.0};
+    int redo = 0;
     if (lane == 0) {
-        V3 nv;
+        double gap = 1.0;
         if (cnt >= 3) {
+            // centred second moments: better conditioned than raw cumulants, equal to them up to rounding
             const double inv = 1.0 / (double)cnt;
             const double mx = sx * inv, my = sy * inv, mz = sz * inv;
             nv = fast_eigen3x3(sxx * inv - mx * mx, sxy * inv - mx * my, sxz * inv - mx * mz, syy * inv - my * my, syz * inv - my * mz,
-                               szz * inv - mz * mz);
+                               szz * inv - mz * mz, &gap);
+            redo = (gap < kIllGap && cnt <= kCanon) ? 1 : 0;
         } else {
-            nv = fast_eigen3x3(1, 0, 0, 1, 0, 1);   // Open3D: covariance = Identity when fewer than 3 neighbours
+            nv = fast_eigen3x3(1, 0, 0, 1, 0, 1, &gap);   // Open3D: covariance = Identity when fewer than 3 neighbours
         }
+    }
+    redo = __shfl_sync(kFull, redo, 0);
+    if (redo) {
+        // Ill-conditioned neighbourhood (e.g. collinear points of one scan ring): the eigenvector amplifies the
+        // rounding of the covariance by 1/gap, so reproduce Open3D's arithmetic exactly: raw-coordinate cumulants,
+        // summed sequentially in ascending (d2, index) order (the k-NN result order), no FMA contraction.
+        double* key_d2 = reinterpret_cast<double*>(wmem);
+        int* key_idx = reinterpret_cast<int*>(wmem + kCanon * 8);
+        int* key_pos = reinterpret_cast<int*>(wmem + kCanon * 12);
+        int* order = reinterpret_cast<int*>(wmem + kCanon * 16);
+        __syncwarp();
+        int m = 0;
+        for (int cc = 0; cc < ncell; ++cc) {
+            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+            for (unsigned t = cst; t < cen; t += 32) {
+                const unsigned j = t + lane;
+                double x, y, z, d2 = INFINITY;
+                int idx = 0;
+                if (j < cen) {
+                    load_rec(recs + j, x, y, z, idx);
+                    d2 = sqdist(qx, qy, qz, x, y, z);
+                }
+                const bool sel = d2 < r2 && !key_less(tau_d2, tau_idx, d2, idx);
+                const unsigned msk = __ballot_sync(kFull, sel);
+                if (sel) {
+                    const int slot = m + __popc(msk & ((1u << lane) - 1u));
+                    key_d2[slot] = d2; key_idx[slot] = idx; key_pos[slot] = (int)j;
+                }
+                m += __popc(msk);
+            }
+        }
+        __syncwarp();
+        for (int a = lane; a < m; a += 32) {      // rank sort: keys are distinct (index breaks ties)
+            const double d2a = key_d2[a];
+            const int ia = key_idx[a];
+            int rank = 0;
+            for (int b = 0; b < m; ++b) rank += key_less(key_d2[b], key_idx[b], d2a, ia) ? 1 : 0;
+            order[rank] = key_pos[a];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
+            for (int t = 0; t < m; ++t) {
+                double x, y, z;
+                int idx;
+                load_rec(recs + order[t], x, y, z, idx);
+                c0 = __dadd_rn(c0, x); c1 = __dadd_rn(c1, y); c2 = __dadd_rn(c2, z);
+                c3 = __dadd_rn(c3, __dmul_rn(x, x)); c4 = __dadd_rn(c4, __dmul_rn(x, y)); c5 = __dadd_rn(c5, __dmul_rn(x, z));
+                c6 = __dadd_rn(c6, __dmul_rn(y, y)); c7 = __dadd_rn(c7, __dmul_rn(y, z)); c8 = __dadd_rn(c8, __dmul_rn(z, z));
+            }
+            const double dn = (double)m;
+            c0 = __ddiv_rn(c0, dn); c1 = __ddiv_rn(c1, dn); c2 = __ddiv_rn(c2, dn); c3 = __ddiv_rn(c3, dn); c4 = __ddiv_rn(c4, dn);
+            c5 = __ddiv_rn(c5, dn); c6 = __ddiv_rn(c6, dn); c7 = __ddiv_rn(c7, dn); c8 = __ddiv_rn(c8, dn);
+            double gap;
+            nv = fast_eigen3x3(__dsub_rn(c3, __dmul_rn(c0, c0)), __dsub_rn(c4, __dmul_rn(c0, c1)), __dsub_rn(c5, __dmul_rn(c0, c2)),
+                               __dsub_rn(c6, __dmul_rn(c1, c1)), __dsub_rn(c7, __dmul_rn(c1, c2)), __dsub_rn(c8, __dmul_rn(c2, c2)), &gap);
+        }
+    }
+    if (lane == 0) {
         if (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) == 0.0) nv = {0.0, 0.0, 1.0};
         reinterpret_cast<double4*>(s.normals)[p] = make_double4(nv.x, nv.y, nv.z, 0.0);
         s.nn_count[p] = cnt;
@@ -302,8 +379,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
 void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow) {
     if (n_scans == 0 || cap_max == 0) return;
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
-    if (any_narrow) L.launch(k_normals<false>, grid, block, d_scans, np);
-    if (any_wide) L.launch(k_normals<true>, grid, block, d_scans, np);
+    const size_t smem = (size_t)kNrmWarps * kWarpSmem;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_normals<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (any_narrow) L.launch_smem(k_normals<false>, grid, block, smem, d_scans, np);
+    if (any_wide) L.launch_smem(k_normals<true>, grid, block, smem, d_scans, np);
 }
 
 }  // namespace arvc

