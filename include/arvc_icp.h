@@ -18,6 +18,7 @@
 #ifndef ARVC_ICP_H
 #define ARVC_ICP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -46,6 +47,10 @@ void* arvc_stream(arvc_ctx* ctx);                 /* the context's cudaStream_t 
 int arvc_version(void);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t arvc_kernel_launches(const arvc_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the context stream (bench.py's roofline line).  enable(1) starts
+ * recording every launch, report() synchronises and writes "name,launches,total_ms\n" lines into buf. */
+int arvc_profile_enable(arvc_ctx* ctx, int on);
+int arvc_profile_report(arvc_ctx* ctx, char* buf, size_t cap);
 
 /* --- scans -----------------------------------------------------------------------------------------
  * Replaces KeyFrame.load_pointcloud's result handed to Open3D (keyframemanager/keyframe.py:41-45): the
@@ -53,6 +58,10 @@ int64_t arvc_kernel_launches(const arvc_ctx* ctx);
  * The _f64 variant is for PCD files with double fields.  Asynchronous w.r.t. the host when `xyz` is pinned. */
 int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n);
 int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n);
+/* Forget the cached preprocessing of a scan (host-side flag only).  The reference never sets
+ * KeyFrame.pre_processed (keyframe.py:39,114), i.e. every pre_process() call redoes the work; this engine caches by
+ * scan id and parameters, and this call restores the reference's "redo" behaviour (used by bench.py). */
+int arvc_scan_invalidate(arvc_ctx* ctx, int64_t scan_id);
 /* KeyFrame.unload_pointcloud (keyframe.py:61-72): drop every device buffer of the scan. */
 int arvc_scan_free(arvc_ctx* ctx, int64_t scan_id);
 

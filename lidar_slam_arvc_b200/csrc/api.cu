@@ -242,6 +242,47 @@ int arvc_sync(arvc_ctx* ctx) {
 void* arvc_stream(arvc_ctx* ctx) { return ctx ? (void*)ctx->L.stream : nullptr; }
 int64_t arvc_kernel_launches(const arvc_ctx* ctx) { return ctx ? ctx->L.launches : 0; }
 
+int arvc_profile_enable(arvc_ctx* ctx, int on) {
+    if (!ctx) return ARVC_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->L.stream);
+    for (auto& r : ctx->L.recs) { ctx->L.pool.push_back(r.a); ctx->L.pool.push_back(r.b); }
+    ctx->L.recs.clear();
+    ctx->L.profile = on != 0;
+    return ARVC_OK;
+}
+
+int arvc_profile_report(arvc_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return ARVC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : ctx->L.recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& a = agg[r.name]; a.first += 1; a.second += ms; }
+        ctx->L.pool.push_back(r.a); ctx->L.pool.push_back(r.b);
+    }
+    ctx->L.recs.clear();
+    std::string out;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s,%lld,%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (out.size() + 1 > cap) return ctx->fail(ARVC_E_ARG, "profile_report: buffer too small");
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return ARVC_OK;
+}
+
+int arvc_scan_invalidate(arvc_ctx* ctx, int64_t scan_id) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s) return ctx->fail(ARVC_E_STATE, "scan_invalidate: unknown scan id");
+    s->preprocessed = false;
+    s->has_normals = false;
+    return ARVC_OK;
+}
+
 int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n) { return upload(ctx, scan_id, xyz, n, false); }
 int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n) { return upload(ctx, scan_id, xyz, n, true); }
 
@@ -350,7 +391,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     // ---- run
     unsigned tmax = 0;
     for (Scan* s : todo) tmax = std::max(tmax, s->dev.table_mask + 1u);
-    ctx->L.launch(k_clear_scan, dim3(std::min(256u, (tmax + 255u) / 256u), (unsigned)todo.size()), dim3(256), (const ScanDev*)d_batch);
+    ctx->L.launch("clear_scan", k_clear_scan, dim3(std::min(256u, (tmax + 255u) / 256u), (unsigned)todo.size()), dim3(256), (const ScanDev*)d_batch);
     run_preprocess(ctx->L, d_batch, (int)todo.size(), cap_max, fp, vp, voxel_on);
     if (want_normals) run_normals(ctx->L, d_batch, (int)todo.size(), cap_max, np, any_wide, any_narrow);
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -16,15 +17,29 @@ struct Launcher {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     cudaError_t err = cudaSuccess;
-    template <typename... KArgs, typename... Args>
-    void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
-        launch_smem(kernel, grid, block, 0, args...);
+    // optional per-kernel timing with CUDA events on the launching stream (arvc_profile_*)
+    bool profile = false;
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
     }
     template <typename... KArgs, typename... Args>
-    void launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    void launch(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+        launch_smem(name, kernel, grid, block, 0, args...);
+    }
+    template <typename... KArgs, typename... Args>
+    void launch_smem(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
         if (err != cudaSuccess) return;
         if (grid.x == 0 || grid.y == 0) return;
+        Rec r{name, nullptr, nullptr};
+        if (profile) { r.a = get_event(); r.b = get_event(); cudaEventRecord(r.a, stream); }
         kernel<<<grid, block, smem, stream>>>(args...);
+        if (profile) { cudaEventRecord(r.b, stream); recs.push_back(r); }
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) err = e;
         ++launches;

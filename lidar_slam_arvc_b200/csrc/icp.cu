@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
 
 template <int METHOD>
 static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, const IcpParams& ip, int pass, int combos_mask) {
-    if (combos_mask & 1) L.launch(k_icp_pass<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch(k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch(k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch(k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 1) L.launch("icp_pass", k_icp_pass<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 2) L.launch("icp_pass", k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 4) L.launch("icp_pass", k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 8) L.launch("icp_pass", k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
 }
 
 // combos_mask bit (2*src_wide + tgt_wide) set when some pair of the batch has that record-type combination

@@ -386,8 +386,8 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
         cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (any_narrow) L.launch_smem(k_normals<false>, grid, block, smem, d_scans, np);
-    if (any_wide) L.launch_smem(k_normals<true>, grid, block, smem, d_scans, np);
+    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem, d_scans, np);
+    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem, d_scans, np);
 }
 
 }  // namespace arvc

@@ -243,9 +243,9 @@ static int radix_sort(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_
     const int nblk = (cap_max + kSortTile - 1) / kSortTile;
     int src = 0;
     for (int shift = 0; shift < nbits; shift += 8) {
-        L.launch(k_radix_hist<K>, dim3(nblk, n_scans), dim3(kSortThreads), d_scans, cnt_index, src, shift);
-        L.launch(k_radix_scan, dim3(n_scans), dim3(1024), d_scans, cnt_index);
-        L.launch(k_radix_scatter<K>, dim3(nblk, n_scans), dim3(kSortThreads), d_scans, cnt_index, src, shift);
+        L.launch("radix_hist", k_radix_hist<K>, dim3(nblk, n_scans), dim3(kSortThreads), d_scans, cnt_index, src, shift);
+        L.launch("radix_scan", k_radix_scan, dim3(n_scans), dim3(1024), d_scans, cnt_index);
+        L.launch("radix_scatter", k_radix_scatter<K>, dim3(nblk, n_scans), dim3(kSortThreads), d_scans, cnt_index, src, shift);
         src ^= 1;
     }
     return src;
@@ -417,18 +417,18 @@ void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_ma
     if (n_scans == 0 || cap_max == 0) return;
     const int nb1024 = (cap_max + kCompactBlock - 1) / kCompactBlock;
     const int nb256 = (cap_max + 255) / 256;
-    L.launch(k_filter_count, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, fp);
-    L.launch(k_filter_scatter, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, fp, (int)voxel_on);
+    L.launch("filter_count", k_filter_count, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, fp);
+    L.launch("filter_scatter", k_filter_scatter, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, fp, (int)voxel_on);
     if (voxel_on) {
-        L.launch(k_voxel_bbox, dim3(min(nb256, 64), n_scans), dim3(256), d_scans);
-        L.launch(k_voxel_keys, dim3(nb256, n_scans), dim3(256), d_scans, vp);
+        L.launch("voxel_bbox", k_voxel_bbox, dim3(min(nb256, 64), n_scans), dim3(256), d_scans);
+        L.launch("voxel_keys", k_voxel_keys, dim3(nb256, n_scans), dim3(256), d_scans, vp);
         const int src = radix_sort<unsigned long long>(L, d_scans, n_scans, cap_max, CNT_NFILT, vp.bx + vp.by + vp.bz);
-        L.launch(k_voxel_heads_count, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, src);
-        L.launch(k_voxel_reduce, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, src, vp);
+        L.launch("voxel_heads_count", k_voxel_heads_count, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, src);
+        L.launch("voxel_reduce", k_voxel_reduce, dim3(nb1024, n_scans), dim3(kCompactBlock), d_scans, src, vp);
     }
-    L.launch(k_morton_keys, dim3(nb256, n_scans), dim3(256), d_scans, (int)voxel_on);
+    L.launch("morton_keys", k_morton_keys, dim3(nb256, n_scans), dim3(256), d_scans, (int)voxel_on);
     const int src = radix_sort<unsigned>(L, d_scans, n_scans, cap_max, CNT_NPTS, 3 * kMortonBits);
-    L.launch(k_gather_build, dim3(nb256, n_scans), dim3(256), d_scans, src, (int)voxel_on);
+    L.launch("gather_build", k_gather_build, dim3(nb256, n_scans), dim3(256), d_scans, src, (int)voxel_on);
 }
 
 }  // namespace arvc

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "arvc_kernel_launches", "arvc_scan_upload_f32", "arvc_scan_upload_f64", "arvc_scan_free", "arvc_scan_preprocess",
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
-    "arvc_host_alloc", "arvc_host_free",
+    "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate",
 ]
 
 
@@ -81,6 +81,9 @@ def load_library():
     lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
     lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
     lib.arvc_icp_trace.argtypes = [vp, c.c_int64, c.c_int64, dp, c.POINTER(IcpParams), ip, dp, dp, dp, ip, c.POINTER(ResultRecord)]
+    lib.arvc_profile_enable.argtypes = [vp, c.c_int]
+    lib.arvc_profile_report.argtypes = [vp, c.c_char_p, c.c_size_t]
+    lib.arvc_scan_invalidate.argtypes = [vp, c.c_int64]
     lib.arvc_host_alloc.argtypes = [c.c_size_t]
     lib.arvc_host_alloc.restype = vp
     lib.arvc_host_free.argtypes = [vp]
@@ -236,6 +239,23 @@ class Engine:
         out = np.zeros(1, dtype=RESULT_DTYPE)
         ctypes.memmove(out.ctypes.data, ctypes.byref(rec), 160)
         return {"corr": corr, "T": trT[:k], "fitness": trf[:k], "rmse": trr[:k], "passes": k, "result": out[0]}
+
+    def invalidate(self, scan_ids):
+        for k in np.atleast_1d(scan_ids):
+            self._ck(self.lib.arvc_scan_invalidate(self.h, int(k)))
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.arvc_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since profile_enable(); synchronises."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._ck(self.lib.arvc_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split(",")
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def sync(self):
         self._ck(self.lib.arvc_sync(self.h))
