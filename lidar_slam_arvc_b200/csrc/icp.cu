@@ -15,6 +15,63 @@ namespace {
 
 struct Best { double d2; int idx; int pos; };
 
+constexpr int kLeafMax = 48;   // cells with more points than this are descended octree-style instead of scanned
+
+template <bool TW>
+__device__ __forceinline__ void scan_run(const typename RecT<TW>::type* __restrict__ recs, unsigned st, unsigned en, double sx, double sy,
+                                         double sz, Best& b) {
+    for (unsigned p = st; p < en; ++p) {
+        double x, y, z;
+        int idx;
+        load_rec(recs + p, x, y, z, idx);
+        const double d2 = sqdist(sx, sy, sz, x, y, z);
+        if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = (int)p; }
+    }
+}
+
+__device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
+    const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
+    const double ddx = fmax(0.0, fmax(bx0 - sx, sx - (bx0 + cl)));
+    const double ddy = fmax(0.0, fmax(by0 - sy, sy - (by0 + cl)));
+    const double ddz = fmax(0.0, fmax(bz0 - sz, sz - (bz0 + cl)));
+    return ddx * ddx + ddy * ddy + ddz * ddz;
+}
+
+// Branch-and-bound descent of one big cell (level l > 0): its eight children are the level l-1 cells with
+// prefix*8+k, visited nearest octant first and pruned by box distance against the best so far.  Keeps queries
+// whose nearest neighbour is metres away (occlusion shadows) from scanning thousands of points linearly.
+template <bool TW>
+__device__ __noinline__ void descend_cell(const ScanDev& tgt, double sx, double sy, double sz, Best& b, int l, int cx, int cy, int cz) {
+    typedef typename RecT<TW>::type Rec;
+    const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
+    const GridSpec g = tgt.grid;
+    int fcx[kMortonBits + 1], fcy[kMortonBits + 1], fcz[kMortonBits + 1];
+    unsigned char fk[kMortonBits + 1], fnear[kMortonBits + 1];
+    int depth = 0;
+    auto near_octant = [&](int level, int x, int y, int z) -> unsigned char {
+        const double cl = g.c0 * (double)(1 << level), h = 0.5 * cl;
+        return (unsigned char)(((sx >= g.ox + x * cl + h) ? 4 : 0) | ((sy >= g.oy + y * cl + h) ? 2 : 0) | ((sz >= g.oz + z * cl + h) ? 1 : 0));
+    };
+    fcx[0] = cx; fcy[0] = cy; fcz[0] = cz; fk[0] = 0; fnear[0] = near_octant(l, cx, cy, cz);
+    while (depth >= 0) {
+        if (fk[depth] == 8) { --depth; continue; }
+        const unsigned child = fnear[depth] ^ ((0x76534210u >> (4 * fk[depth])) & 7u);   // 0,1,2,4,3,5,6,7 axis flips
+        ++fk[depth];
+        const int cl_level = l - depth - 1;
+        const int ccx = 2 * fcx[depth] + ((child >> 2) & 1), ccy = 2 * fcy[depth] + ((child >> 1) & 1), ccz = 2 * fcz[depth] + (child & 1);
+        const double cl = g.c0 * (double)(1 << cl_level);
+        if (box_d2(g, ccx, ccy, ccz, cl, sx, sy, sz) > b.d2 * (1.0 + 1e-9) + 1e-12) continue;
+        unsigned st, en;
+        if (!grid_lookup(tgt.table, tgt.table_mask, cl_level, morton3(ccx, ccy, ccz), st, en)) continue;
+        if (cl_level == 0 || en - st <= (unsigned)kLeafMax) {
+            scan_run<TW>(recs, st, en, sx, sy, sz, b);
+        } else {
+            ++depth;
+            fcx[depth] = ccx; fcy[depth] = ccy; fcz[depth] = ccz; fk[depth] = 0; fnear[depth] = near_octant(cl_level, ccx, ccy, ccz);
+        }
+    }
+}
+
 // Exact nearest neighbour of (sx,sy,sz) among the target records, under the (d2, cloud index) order.
 // On entry `b` holds an exclusive upper bound (candidates must be lexicographically smaller).
 template <bool TW>
@@ -31,25 +88,20 @@ __device__ __forceinline__ void nn_search(const ScanDev& tgt, double sx, double 
         const int x0 = cell_coord(sx - r, g.ox, g.inv_c0) >> l, x1 = cell_coord(sx + r, g.ox, g.inv_c0) >> l;
         const int y0 = cell_coord(sy - r, g.oy, g.inv_c0) >> l, y1 = cell_coord(sy + r, g.oy, g.inv_c0) >> l;
         const int z0 = cell_coord(sz - r, g.oz, g.inv_c0) >> l, z1 = cell_coord(sz + r, g.oz, g.inv_c0) >> l;
-        for (int cz = z0; cz <= z1; ++cz)
-            for (int cy = y0; cy <= y1; ++cy)
-                for (int cx = x0; cx <= x1; ++cx) {
-                    // skip cells whose box is farther than the current best (conservative slack)
-                    const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
-                    const double ddx = fmax(0.0, fmax(bx0 - sx, sx - (bx0 + cl)));
-                    const double ddy = fmax(0.0, fmax(by0 - sy, sy - (by0 + cl)));
-                    const double ddz = fmax(0.0, fmax(bz0 - sz, sz - (bz0 + cl)));
-                    if (ddx * ddx + ddy * ddy + ddz * ddz > b.d2 * (1.0 + 1e-9) + 1e-12) continue;
-                    unsigned st, en;
-                    if (!grid_lookup(tab, mask, l, morton3(cx, cy, cz), st, en)) continue;
-                    for (unsigned p = st; p < en; ++p) {
-                        double x, y, z;
-                        int idx;
-                        load_rec(recs + p, x, y, z, idx);
-                        const double d2 = sqdist(sx, sy, sz, x, y, z);
-                        if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = (int)p; }
-                    }
-                }
+        // the cell holding the query first: it usually yields the bound that prunes the others
+        const int hx = min(max(cell_coord(sx, g.ox, g.inv_c0) >> l, x0), x1), hy = min(max(cell_coord(sy, g.oy, g.inv_c0) >> l, y0), y1),
+                  hz = min(max(cell_coord(sz, g.oz, g.inv_c0) >> l, z0), z1);
+        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
+        const int home = (hx - x0) + nx * ((hy - y0) + ny * (hz - z0));
+        for (int t = 0; t < ncell; ++t) {
+            const int c = t == 0 ? home : (t <= home ? t - 1 : t);
+            const int cx = x0 + c % nx, cy = y0 + (c / nx) % ny, cz = z0 + c / (nx * ny);
+            if (box_d2(g, cx, cy, cz, cl, sx, sy, sz) > b.d2 * (1.0 + 1e-9) + 1e-12) continue;   // conservative slack
+            unsigned st, en;
+            if (!grid_lookup(tab, mask, l, morton3(cx, cy, cz), st, en)) continue;
+            if (l > 0 && en - st > (unsigned)kLeafMax) descend_cell<TW>(tgt, sx, sy, sz, b, l, cx, cy, cz);
+            else scan_run<TW>(recs, st, en, sx, sy, sz, b);
+        }
         // every point within min(best radius, cl) has been seen: exact as soon as the best lies within cl
         if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) return;
     }

@@ -1,0 +1,112 @@
+"""KeyFrameManager: indexable container of KeyFrames that dispatches `method` to the registration routine.
+
+Same public surface as the reference's keyframemanager/keyframemanager.py:9-75 (constructor, add_keyframe(s),
+load/unload_pointcloud, pre_process, compute_transformation); the GUI methods (draw_*, visualize_*) are not part
+of the hot path.  Extension for batched callers (loop closing): `pre_process_many` and
+`compute_transformations`, which issue ONE device batch for many independent pairs.
+"""
+import numpy as np
+
+from config import ICP_PARAMETERS
+from keyframemanager.keyframe import KeyFrame, PointCloud
+from lidar_slam_arvc_b200 import runtime
+from lidar_slam_arvc_b200.engine import P2P, P2PLANE
+from lidar_slam_arvc_b200.homogeneousmatrix import result_type
+
+
+class KeyFrameManager():
+    def __init__(self, directory, scan_times, voxel_size, method='icppointplane'):
+        """given a list of scan times (ROS times), each pcd is read on demand"""
+        self.directory = directory
+        self.scan_times = scan_times
+        self.keyframes = []
+        self.voxel_size = voxel_size
+        self.method = method
+        self.show_registration_result = False
+
+    def add_keyframes(self, keyframe_sampling):
+        for i in range(0, len(self.scan_times), keyframe_sampling):
+            print("Keyframemanager: Adding Keyframe: ", i, "out of: ", len(self.scan_times), end='\r')
+            self.add_keyframe(i)
+
+    def add_keyframe(self, index):
+        print('Adding keyframe with scan_time: ', self.scan_times[index])
+        kf = KeyFrame(directory=self.directory, scan_time=self.scan_times[index], voxel_size=self.voxel_size)
+        self.keyframes.append(kf)
+
+    def load_pointclouds(self):
+        for i in range(0, len(self.keyframes)):
+            print("Keyframemanager: Loading Pointcloud: ", i, "out of: ", len(self.keyframes), end='\r')
+            self.keyframes[i].load_pointcloud()
+
+    def load_pointcloud(self, i):
+        self.keyframes[i].load_pointcloud()
+
+    def unload_pointcloud(self, i):
+        self.keyframes[i].unload_pointcloud()
+
+    def pre_process(self, index):
+        self.keyframes[index].pre_process(method=self.method)
+
+    def compute_transformation(self, i, j, Tij):
+        """ICP with target = keyframes[i], source = keyframes[j], initial guess Tij (HomogeneousMatrix); returns iTj."""
+        if self.method == 'icppointpoint':
+            transform = self.keyframes[i].local_registration_simple(self.keyframes[j], initial_transform=Tij.array,
+                                                                    option='pointpoint')
+        elif self.method == 'icppointplane':
+            transform = self.keyframes[i].local_registration_simple(self.keyframes[j], initial_transform=Tij.array,
+                                                                    option='pointplane')
+        elif self.method == 'icp2planes':
+            transform = self.keyframes[i].local_registration_two_planes(self.keyframes[j], initial_transform=Tij.array)
+        elif self.method == 'fpfh':
+            transform = self.keyframes[i].global_registration(self.keyframes[j])
+        else:
+            print('Unknown registration method')
+            transform = None
+        return transform
+
+    # ------------------------------------------------------------------ batched extensions
+    def pre_process_many(self, indices):
+        """pre_process() of many keyframes in one device batch (same results as calling pre_process one by one)."""
+        if self.method not in ('icppointpoint', 'icppointplane'):
+            raise NotImplementedError("batched preprocessing supports icppointpoint / icppointplane")
+        kfs = [self.keyframes[i] for i in indices]
+        if not kfs:
+            return
+        for kf in kfs:
+            kf._require_loaded()
+        runtime.get_engine().preprocess([kf._scan_id for kf in kfs], kfs[0]._params(self.method == 'icppointplane'))
+        for kf in kfs:
+            kf._preprocessed_on_device = True
+            kf._filtered_cache = None
+
+    def compute_transformations(self, pairs, Tijs):
+        """[(i, j), ...] and initial guesses -> list of iTj, one device batch.  Each keyframe's `last_result`-style record
+        is returned alongside: (transforms, records)."""
+        if self.method not in ('icppointpoint', 'icppointplane'):
+            raise NotImplementedError("batched registration supports icppointpoint / icppointplane")
+        eng = runtime.get_engine()
+        method = P2P if self.method == 'icppointpoint' else P2PLANE
+        ip = eng.make_icp_params(method, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
+                                 ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)
+        tg = [self.keyframes[i]._scan_id for i, _ in pairs]
+        sr = [self.keyframes[j]._scan_id for _, j in pairs]
+        init = np.array([np.eye(4) if (T is None or getattr(T, "array", T) is None) else np.asarray(getattr(T, "array", T), dtype=np.float64)
+                         for T in Tijs]).reshape(-1, 4, 4)
+        rec = eng.icp_batch(tg, sr, init, ip)
+        H = result_type()
+        return [H(np.array(r["T"])) for r in rec], rec
+
+    # ------------------------------------------------------------------ map building without the GUI (host concatenation)
+    def build_map(self, global_transforms, keyframe_sampling=10, radii=None, heights=None):
+        if radii is None:
+            radii = [0.5, 35.0]
+        if heights is None:
+            heights = [-120.0, 120.0]
+        sampled = [global_transforms[i] for i in range(0, len(global_transforms), keyframe_sampling)]
+        out = PointCloud()
+        for i, kf in enumerate(self.keyframes):
+            kf.filter_radius_height(radii=radii, heights=heights)
+            kf.down_sample()
+            out = out + kf.transform(T=sampled[i].array)
+        return out

@@ -1,0 +1,104 @@
+"""Duck-type of artelib.homogeneousmatrix.HomogeneousMatrix — the return type of
+KeyFrameManager.compute_transformation (reference: artelib/homogeneousmatrix.py:16-107, keyframe.py:259).
+
+When the reference's own `artelib` package is importable (drop-in use inside the reference tree) that class is
+used, so callers get exactly the type they expect; otherwise this numpy-only class offers the members the
+scan-matching callers touch (run_scanmatcher.py:207-208,221,230; loopclosing.py:89,120-122,182):
+`.array`, `*`, `.inv()`, `.pos()`, `.Q()`, `.euler()`, `.t2v()`, `.print_nice()`.
+"""
+import numpy as np
+
+
+def rot2quaternion(R):
+    """[qw, qx, qy, qz] of a rotation matrix; same branch structure as the reference's artelib.tools.rot2quaternion
+    (:110-172): positive scalar part from the trace, vector part scaled from the dominant diagonal entry."""
+    R = np.asarray(R, dtype=np.float64)[0:3, 0:3]
+    s = np.sqrt(max(0.0, np.trace(R) + 1.0)) / 2.0
+    k = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    d = int(np.argmax(np.diag(R)))
+    if d == 0:
+        k1 = np.array([R[0, 0] - R[1, 1] - R[2, 2] + 1, R[1, 0] + R[0, 1], R[2, 0] + R[0, 2]])
+    elif d == 1:
+        k1 = np.array([R[1, 0] + R[0, 1], R[1, 1] - R[0, 0] - R[2, 2] + 1, R[2, 1] + R[1, 2]])
+    else:
+        k1 = np.array([R[2, 0] + R[0, 2], R[2, 1] + R[1, 2], R[2, 2] - R[0, 0] - R[1, 1] + 1])
+    sgn = 1.0 if k[d] >= 0 else -1.0
+    k = k + sgn * k1
+    nm = np.linalg.norm(k)
+    if nm == 0:
+        return np.array([1.0, 0.0, 0.0, 0.0])
+    return np.hstack((s, np.sqrt(max(0.0, 1 - s ** 2)) / nm * k))
+
+
+def rot2euler_zyx(R):
+    """(alpha, beta, gamma) with R = Rx(alpha) Ry(beta) Rz(gamma) convention is the reference's; here the common
+    XYZ-fixed decomposition R = Rz(g) Ry(b) Rx(a) is returned as [a, b, g] for diagnostics only."""
+    R = np.asarray(R, dtype=np.float64)
+    b = -np.arcsin(np.clip(R[2, 0], -1, 1))
+    a = np.arctan2(R[2, 1], R[2, 2])
+    g = np.arctan2(R[1, 0], R[0, 0])
+    return np.array([a, b, g])
+
+
+class HomogeneousMatrix:
+    def __init__(self, *args):
+        if len(args) == 0:
+            self.array = np.eye(4)
+        elif len(args) == 1:
+            a = args[0]
+            self.array = a.toarray() if isinstance(a, HomogeneousMatrix) else (a if isinstance(a, np.ndarray) else np.array(a))
+        else:
+            raise TypeError("HomogeneousMatrix(position, orientation) needs the reference's artelib package")
+
+    def __str__(self):
+        return str(self.array)
+
+    def toarray(self):
+        return self.array
+
+    def print_nice(self, precision=3):
+        print(np.array_str(self.array, precision=precision, suppress_small=True))
+
+    def inv(self):
+        return HomogeneousMatrix(np.linalg.inv(self.array))
+
+    def Q(self):
+        return rot2quaternion(self.array)
+
+    def R(self):
+        return self.array[0:3, 0:3]
+
+    def pos(self):
+        return self.array[0:3, 3]
+
+    def euler(self):
+        return rot2euler_zyx(self.array)
+
+    def __mul__(self, other):
+        if isinstance(other, HomogeneousMatrix) or hasattr(other, "array"):
+            return HomogeneousMatrix(np.dot(self.array, other.array))
+        return NotImplemented
+
+    def __add__(self, other):
+        return HomogeneousMatrix(self.array + other.array)
+
+    def __sub__(self, other):
+        return HomogeneousMatrix(self.array - other.array)
+
+    def __getitem__(self, item):
+        return self.array[item[0], item[1]]
+
+    def t2v(self, n=2):
+        if n == 2:
+            return np.array([self.array[0, 3], self.array[1, 3], np.arctan2(self.array[1, 0], self.array[0, 0])])
+        e = rot2euler_zyx(self.array)
+        return np.array([self.array[0, 3], self.array[1, 3], self.array[2, 3], e[0], e[1], e[2]])
+
+
+def result_type():
+    """The class compute_transformation wraps its result in: the reference's own when available."""
+    try:
+        from artelib.homogeneousmatrix import HomogeneousMatrix as RefH   # noqa: WPS433 (reference tree on sys.path)
+        return RefH
+    except Exception:
+        return HomogeneousMatrix

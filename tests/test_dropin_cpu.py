@@ -1,0 +1,126 @@
+"""Host logic of the drop-in boundary, on CPU: PCD I/O, the HomogeneousMatrix duck-type against the reference's own
+artelib (golden vectors), the config singleton, and — when /root/reference is present — the reference's UNMODIFIED
+run_scanmatcher.scanmatcher() running on top of the drop-in keyframemanager (arithmetic supplied by the oracle test
+double, since there is no GPU in this container)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from lidar_slam_arvc_b200 import euroc_synth, pcd, runtime, synth
+from lidar_slam_arvc_b200.homogeneousmatrix import HomogeneousMatrix, rot2quaternion
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "lidar_slam_arvc_b200", "dropin")
+REF = "/root/reference"
+
+
+def test_pcd_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(1000, 3)).astype(np.float32)
+    xyz[3] = np.nan
+    for binary in (True, False):
+        fn = str(tmp_path / ("a_%d.pcd" % binary))
+        pcd.write_pcd_xyz(fn, xyz, binary=binary)
+        back = pcd.read_pcd_xyz(fn)
+        assert back.dtype == np.float32 and back.shape == xyz.shape
+        np.testing.assert_array_equal(back, xyz)
+    # extra fields and float64 coordinates
+    fn = str(tmp_path / "b.pcd")
+    rec = np.zeros(5, dtype=[("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("intensity", "<f4")])
+    rec["x"], rec["y"], rec["z"] = np.arange(5), np.arange(5) * 2.0, 0.1
+    with open(fn, "wb") as f:
+        f.write(b"VERSION 0.7\nFIELDS x y z intensity\nSIZE 8 8 8 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 5\nHEIGHT 1\nPOINTS 5\nDATA binary\n")
+        f.write(rec.tobytes())
+    back = pcd.read_pcd_xyz(fn)
+    assert back.dtype == np.float64
+    np.testing.assert_array_equal(back[:, 1], np.arange(5) * 2.0)
+    empty = str(tmp_path / "e.pcd")
+    pcd.write_pcd_xyz(empty, np.zeros((0, 3)))
+    assert pcd.read_pcd_xyz(empty).shape == (0, 3)
+
+
+def test_homogeneous_matrix_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "se3_helpers.npz"))
+    for T, Ti, P, q in zip(g["mats"], g["invs"], g["prods"], g["quats"]):
+        H = HomogeneousMatrix(T)
+        np.testing.assert_allclose(H.inv().array, Ti, atol=1e-12)
+        np.testing.assert_allclose((H * H.inv() * H).array, P, atol=1e-12)
+        np.testing.assert_allclose(rot2quaternion(T), q, atol=1e-12)
+        np.testing.assert_array_equal(H.pos(), T[:3, 3])
+
+
+def test_config_singleton_has_reference_fields():
+    sys.path.insert(0, DROPIN)
+    try:
+        for m in [k for k in sys.modules if k == "config" or k.startswith("config.")]:
+            del sys.modules[m]
+        from config import ICP_PARAMETERS as P
+        assert (P.max_radius, P.min_radius, P.min_height, P.max_height) == (35, 0.5, -1.0, 50.0)
+        assert P.voxel_size is None and P.max_nn == 300 and P.distance_threshold == 10.0
+        assert (P.relative_fitness, P.relative_rmse, P.max_iteration) == (1e-6, 1e-6, 30)
+        if os.path.isdir(REF):
+            import yaml
+            ref = yaml.safe_load(open(os.path.join(REF, "config", "icp_parameters.yaml")))
+            ours = yaml.safe_load(open(os.path.join(DROPIN, "config", "icp_parameters.yaml")))
+            ours.pop("icp_criteria")
+            assert ours == ref                           # same schema, same defaults
+    finally:
+        sys.path.remove(DROPIN)
+
+
+def _stub_missing_modules():
+    for name in ("matplotlib", "matplotlib.pyplot", "pyproj", "open3d"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if not hasattr(sys.modules["pyproj"], "Proj"):
+        sys.modules["pyproj"].Proj = lambda *a, **k: None
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_reference_scanmatcher_runs_unmodified_on_dropin(tmp_path):
+    """run_scanmatcher.scanmatcher(directory) — the reference's own driver, byte for byte — on the drop-in classes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_engine import OracleEngine
+    from oracle import oracle as orc
+    seq = synth.Sequence(5, synth.TINY_16, start=30.0)
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq)
+    saved_path, saved_mods = list(sys.path), dict(sys.modules)
+    fake = OracleEngine()
+    runtime.set_engine(fake)
+    try:
+        _stub_missing_modules()
+        for m in [k for k in sys.modules if k.split(".")[0] in ("config", "keyframemanager")]:
+            del sys.modules[m]
+        sys.path.insert(0, REF)          # reference second ...
+        sys.path.insert(0, DROPIN)       # ... drop-in first
+        import run_scanmatcher
+        import keyframemanager.keyframemanager as kfm
+        assert kfm.__file__.startswith(DROPIN)
+        run_scanmatcher.scanmatcher(directory=d)
+        import pandas as pd
+        rel = pd.read_csv(os.path.join(d, "robot0", "scanmatcher", "scanmatcher_relative.csv"))
+        glob = pd.read_csv(os.path.join(d, "robot0", "scanmatcher", "scanmatcher_global.csv"))
+        assert len(rel) == 4 and len(glob) == 5
+        assert list(rel.columns)[1:] == ["#timestamp [ns]", "x", "y", "z", "qx", "qy", "qz", "qw"]
+        np.testing.assert_array_equal(rel["#timestamp [ns]"].to_numpy(), times[:4])
+        # the relative transforms written by the reference driver are the oracle's ICP results for (i, i+1), init = odometry
+        pre = [orc.preprocess(s) for s in seq.scans]
+        for i in range(4):
+            ref = orc.icp(pre[i + 1][0], pre[i][0], pre[i][1], seq.relative_odo(i, i + 1), orc.P2PLANE)
+            np.testing.assert_allclose(rel.loc[i, ["x", "y", "z"]].to_numpy(dtype=float), ref.transformation[:3, 3], atol=1e-6)
+            gt = seq.relative_gt(i, i + 1)
+            assert np.linalg.norm(ref.transformation[:3, 3] - gt[:3, 3]) < 0.05
+        # call pattern of run_scanmatcher.py:191-213: one preprocess per keyframe, one ICP per consecutive pair
+        assert [c for c in fake.calls if c[0] == "icp_batch"] == [("icp_batch", 1)] * 4
+        assert len([c for c in fake.calls if c[0] == "preprocess"]) == 5
+    finally:
+        runtime.set_engine(None)
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]
