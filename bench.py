@@ -72,20 +72,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Summary of the samples that arrived inside [t0, t1] (falls back to the nearest ones for a short window)."""
+        inside = [s for (t, s) in self.samples if t0 <= t <= t1]
+        if not inside and self.samples:
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.samples, key=lambda ts: abs(ts[0] - mid))[1]]
+        return self._summarise(inside)
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def _summarise(self, lines):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in lines:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -202,6 +213,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)      # started well before the timed regions: nvidia-smi start-up stalls the driver
+    clocks.start()
     # ---- warm-up (also fills the stream-ordered memory pool)
     for _ in range(max(args.warmup, 1)):
         upload_all()
@@ -212,10 +225,9 @@ def main():
     # ---- value: scans resident in HBM, device time
     upload_all()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     eng.profile_enable(True)
     l0 = eng.kernel_launches()
+    tw0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -224,9 +236,17 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches() - l0
-    prof = eng.profile_report()
+    prof_raw = eng.profile_report()
+    prof, icp_passes = {}, {}
+    for k, v in prof_raw.items():                      # the engine reports every ICP pass separately
+        if k.startswith("icp_pass_"):
+            icp_passes[k[-2:]] = round(v[1] / v[0], 4)
+            c, t = prof.get("icp_pass", (0, 0.0))
+            prof["icp_pass"] = (c + v[0], t + v[1])
+        else:
+            prof[k] = v
     eng.profile_enable(False)
-    clk = clocks.stop()
+    tw1 = time.perf_counter()
     own = eng.icp_batch(tg, sr, init, ip)          # this rank's own records (cached preprocessing), for the byte model
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -242,6 +262,9 @@ def main():
         rec_all = hot_path()
     barrier()
     e2e_s = time.perf_counter() - t0
+    time.sleep(0.25)
+    clocks.stop()
+    clk = clocks.window(tw0, t0 + e2e_s)
     t_s = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
@@ -274,6 +297,7 @@ def main():
                 "kernel_share_of_device_time": tot_ms / dev_ms if dev_ms > 0 else None,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                 "all_kernels_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+                "icp_pass_avg_ms_by_pass": icp_passes,
                 "note": "working set per pair is L2-resident and the search is FP64/LSU bound; see DESIGN.md"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
@@ -282,7 +306,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": float(t_s.item()) / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-            "mean_icp_updates": float(np.mean(own["updates"])), "points_per_scan": int(n_pts.mean())}
+            "mean_icp_updates": float(np.mean(own["updates"])), "icp_updates": [int(u) for u in own["updates"]], "points_per_scan": int(n_pts.mean())}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -584,6 +585,11 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             ip.max_d = p->max_corr_dist;
             ip.max_d2 = p->max_corr_dist > 0 ? p->max_corr_dist * p->max_corr_dist : 0.0;
             ip.rel_fitness = p->rel_fitness; ip.rel_rmse = p->rel_rmse; ip.max_iter = p->max_iter; ip.method = p->method;
+            {
+                const char* dl = getenv("ARVC_DEFER_LEVEL");   // tuning knob; results do not depend on it
+                ip.defer_level = dl ? atoi(dl) : kMortonBits;   // block-wide phase off by default (measured slower)
+                ip.debug = getenv("ARVC_DEBUG_STATS") ? 1 : 0;
+            }
             run_icp(ctx->L, d_pairs, n_pairs, src_cap_max, ip, combos);
             CK(cudaMemcpyAsync(pb.h_states, d_states, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->L.stream));
         }
@@ -599,6 +605,15 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
     struct Recycle { arvc_ctx* c; PendingBatch& b; ~Recycle() { c->pinned_put(b.h_states, b.h_bytes); b.h_states = nullptr; } } recycle{ctx, pb};
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     int err = 0;
+    if (getenv("ARVC_DEBUG_STATS")) {
+        unsigned long long tot[8] = {0}, tl[8] = {0};
+        long long passes = 0;
+        for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 8; ++k) { tot[k] += pb.h_states[i].dbg[k]; tl[k] += pb.h_states[i].tl[k]; } passes += pb.h_states[i].passes; }
+        fprintf(stderr, "[arvc timeline] blocks=%llu avg cycles: prologue=%.0f union=%.0f fallback=%.0f heavy=%.0f epilogue=%.0f | last-block total avg=%.0f | union: lookup=%.0f scan=%.0f\n", tl[5],
+                (double)tl[0] / tl[5], (double)tl[1] / tl[5], (double)tl[2] / tl[5], (double)tl[3] / tl[5], (double)tl[4] / tl[5], (double)tl[6] / (passes ? passes : 1), (double)tl[7] / tl[5], (double)tot[7] / tl[5]);
+        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu union_cand_l0=%llu cert_l0=%llu cert_l1=%llu fallback=%llu heavy=%llu union_cand_l1=%llu\n",
+                pb.n_pairs, passes, tot[6], tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]);
+    }
     for (int i = 0; i < pb.n_pairs; ++i) {
         const PairState& st = pb.h_states[i];
         err |= st.err;

@@ -58,6 +58,8 @@ struct __align__(16) PairState {
     unsigned ticket;
     int err;                // OR of the two scans' device error flags
     int pad[2];
+    unsigned long long dbg[8];   // search statistics, accumulated over all passes
+    unsigned long long tl[8];    // per-phase clock cycles summed over blocks (debug timeline)
 };
 
 struct PairDev {
@@ -76,6 +78,8 @@ struct IcpParams {
     double rel_fitness, rel_rmse;
     int max_iter;
     int method;
+    int defer_level;        // coarsest grid level the 8-lane search handles itself (farther queries: block-wide phase)
+    int debug;              // collect search statistics / phase timeline into PairState (ARVC_DEBUG_STATS)
 };
 
 constexpr int kSumStride = 32;

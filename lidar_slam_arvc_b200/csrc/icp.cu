@@ -7,6 +7,8 @@
 //
 // Reference semantics restated: keyframemanager/keyframe.py:246-252 -> Open3D RegistrationICP,
 // GetRegistrationResultAndCorrespondences, TransformationEstimationPointToPlane / PointToPoint.
+#include <cstdio>
+
 #include "engine.cuh"
 
 namespace arvc {
@@ -15,19 +17,27 @@ namespace {
 
 struct Best { double d2; int idx; int pos; };
 
-constexpr int kLeafMax = 48;   // cells with more points than this are descended octree-style instead of scanned
-
-template <bool TW>
-__device__ __forceinline__ void scan_run(const typename RecT<TW>::type* __restrict__ recs, unsigned st, unsigned en, double sx, double sy,
-                                         double sz, Best& b) {
-    for (unsigned p = st; p < en; ++p) {
-        double x, y, z;
-        int idx;
-        load_rec(recs + p, x, y, z, idx);
-        const double d2 = sqdist(sx, sy, sz, x, y, z);
-        if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = (int)p; }
-    }
-}
+// ---------------------------------------------------------------------------------------------------
+// Exact nearest neighbour on the multi-resolution hash grid, kG lanes cooperating on one query.
+//
+// Work items are grid cells (level, cx, cy, cz, [start, end)) on a small per-group stack in shared memory:
+//   * the cells of the search ball at the start level are pushed home-cell-first;
+//   * a popped cell is dropped when its box is farther than the best so far, scanned cooperatively
+//     (coalesced 16-byte records, float32 screening, float64 evaluation only for candidates that can win or tie)
+//     when it is small or at the finest level, and otherwise expanded into its eight children - lane r looks
+//     up the r-th nearest octant - which go back on the stack nearest-on-top (branch and bound);
+//   * when the level's ball is exhausted and the best is not yet certified, the search moves one level up.
+// The result is the exact minimiser of (d2, cloud index): d2 evaluated exactly as the oracle evaluates it.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kG = 8;            // lanes per query
+constexpr int kBigRun = 160;     // longer runs are expanded into their children instead of scanned
+constexpr int kStack = 48;       // stack entries per group
+constexpr int kGroupsPerBlock = kIcpBlock / kG;
+constexpr int kUnionLevels = 2;  // finest levels served by the shared-candidate (union) phase
+constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
+constexpr int kStage = 64;        // records staged in shared memory per group and round
+constexpr int kPopBudget = 96;   // stack pops a group spends on one query before deferring it
+constexpr int kMaxRuns = 256;    // cells a deferred query may touch (6^3 = 216 at most)
 
 __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
     const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
@@ -37,73 +47,208 @@ __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int 
     return ddx * ddx + ddy * ddy + ddz * ddz;
 }
 
-// Branch-and-bound descent of one big cell (level l > 0): its eight children are the level l-1 cells with
-// prefix*8+k, visited nearest octant first and pruned by box distance against the best so far.  Keeps queries
-// whose nearest neighbour is metres away (occlusion shadows) from scanning thousands of points linearly.
-template <bool TW>
-__device__ __noinline__ void descend_cell(const ScanDev& tgt, double sx, double sy, double sz, Best& b, int l, int cx, int cy, int cz) {
-    typedef typename RecT<TW>::type Rec;
-    const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
-    const GridSpec g = tgt.grid;
-    int fcx[kMortonBits + 1], fcy[kMortonBits + 1], fcz[kMortonBits + 1];
-    unsigned char fk[kMortonBits + 1], fnear[kMortonBits + 1];
-    int depth = 0;
-    auto near_octant = [&](int level, int x, int y, int z) -> unsigned char {
-        const double cl = g.c0 * (double)(1 << level), h = 0.5 * cl;
-        return (unsigned char)(((sx >= g.ox + x * cl + h) ? 4 : 0) | ((sy >= g.oy + y * cl + h) ? 2 : 0) | ((sz >= g.oz + z * cl + h) ? 1 : 0));
-    };
-    fcx[0] = cx; fcy[0] = cy; fcz[0] = cz; fk[0] = 0; fnear[0] = near_octant(l, cx, cy, cz);
-    while (depth >= 0) {
-        if (fk[depth] == 8) { --depth; continue; }
-        const unsigned child = fnear[depth] ^ ((0x76534210u >> (4 * fk[depth])) & 7u);   // 0,1,2,4,3,5,6,7 axis flips
-        ++fk[depth];
-        const int cl_level = l - depth - 1;
-        const int ccx = 2 * fcx[depth] + ((child >> 2) & 1), ccy = 2 * fcy[depth] + ((child >> 1) & 1), ccz = 2 * fcz[depth] + (child & 1);
-        const double cl = g.c0 * (double)(1 << cl_level);
-        if (box_d2(g, ccx, ccy, ccz, cl, sx, sy, sz) > b.d2 * (1.0 + 1e-9) + 1e-12) continue;
-        unsigned st, en;
-        if (!grid_lookup(tgt.table, tgt.table_mask, cl_level, morton3(ccx, ccy, ccz), st, en)) continue;
-        if (cl_level == 0 || en - st <= (unsigned)kLeafMax) {
-            scan_run<TW>(recs, st, en, sx, sy, sz, b);
-        } else {
-            ++depth;
-            fcx[depth] = ccx; fcy[depth] = ccy; fcz[depth] = ccz; fk[depth] = 0; fnear[depth] = near_octant(cl_level, ccx, ccy, ccz);
-        }
-    }
+// float32 screening threshold for a best-so-far d2 (see DESIGN.md "float32 screening"): narrow target records are
+// exact float32 values, so |d2f - d2| <= 2e-6 d2 + 3.5 sqrt(d2) e + 3 e^2 with e the rounding of the query coordinates.
+__device__ __forceinline__ float screen_thr(double best_d2, float e) {
+    const float b = __double2float_ru(best_d2);
+    return (b * (1.0f + 4e-6f) + 3.6f * e * sqrtf(b) + 3.1f * e * e) * (1.0f + 1e-6f);
 }
 
-// Exact nearest neighbour of (sx,sy,sz) among the target records, under the (d2, cloud index) order.
-// On entry `b` holds an exclusive upper bound (candidates must be lexicographically smaller).
 template <bool TW>
-__device__ __forceinline__ void nn_search(const ScanDev& tgt, double sx, double sy, double sz, Best& b, int level) {
+__device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, int level,
+                                             int defer_level, Best& lb, uint4* __restrict__ stk, float* __restrict__ stk_lb, int gl,
+                                             unsigned gmask) {
     typedef typename RecT<TW>::type Rec;
     const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
     const HashEntry* __restrict__ tab = tgt.table;
-    const unsigned mask = tgt.table_mask;
+    const unsigned tmask = tgt.table_mask;
     const GridSpec g = tgt.grid;
+    const int gshift = (lane_id() / kG) * kG;
+    const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
+    const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
+    double gbest = in_d2;                       // group-wide best d2 (every lane holds the same value)
+    float thr = screen_thr(gbest, e);
+    lb.d2 = in_d2; lb.idx = in_idx; lb.pos = -1;
+    bool heavy = false;
+    int pops = 0;
+
     for (int l = level; l <= g.top_level; ++l) {
+        // queries whose nearest neighbour is far (occlusion shadows) would walk hundreds of cells here, one
+        // dependent lookup after the other: hand them to the block-wide phase with the bound found so far
+        if (l > defer_level || pops > kPopBudget) { heavy = true; break; }
         const double cl = g.c0 * (double)(1 << l);
-        const double br = sqrt(b.d2) * (1.0 + 1e-9) + 1e-12;
+        const double br = sqrt(gbest) * (1.0 + 1e-9) + 1e-12;
         const double r = fmin(br, cl);
         const int x0 = cell_coord(sx - r, g.ox, g.inv_c0) >> l, x1 = cell_coord(sx + r, g.ox, g.inv_c0) >> l;
         const int y0 = cell_coord(sy - r, g.oy, g.inv_c0) >> l, y1 = cell_coord(sy + r, g.oy, g.inv_c0) >> l;
         const int z0 = cell_coord(sz - r, g.oz, g.inv_c0) >> l, z1 = cell_coord(sz + r, g.oz, g.inv_c0) >> l;
-        // the cell holding the query first: it usually yields the bound that prunes the others
         const int hx = min(max(cell_coord(sx, g.ox, g.inv_c0) >> l, x0), x1), hy = min(max(cell_coord(sy, g.oy, g.inv_c0) >> l, y0), y1),
                   hz = min(max(cell_coord(sz, g.oz, g.inv_c0) >> l, z0), z1);
-        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
+        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);     // <= 27
         const int home = (hx - x0) + nx * ((hy - y0) + ny * (hz - z0));
-        for (int t = 0; t < ncell; ++t) {
-            const int c = t == 0 ? home : (t <= home ? t - 1 : t);
-            const int cx = x0 + c % nx, cy = y0 + (c / nx) % ny, cz = z0 + c / (nx * ny);
-            if (box_d2(g, cx, cy, cz, cl, sx, sy, sz) > b.d2 * (1.0 + 1e-9) + 1e-12) continue;   // conservative slack
-            unsigned st, en;
-            if (!grid_lookup(tab, mask, l, morton3(cx, cy, cz), st, en)) continue;
-            if (l > 0 && en - st > (unsigned)kLeafMax) descend_cell<TW>(tgt, sx, sy, sz, b, l, cx, cy, cz);
-            else scan_run<TW>(recs, st, en, sx, sy, sz, b);
+        int top = 0;
+        // push the ball's cells, later rounds first, so that order position 0 (the home cell) ends on top
+        for (int base = ((ncell - 1) / kG) * kG; base >= 0; base -= kG) {
+            const int t = base + gl;
+            bool valid = false;
+            unsigned st = 0, en = 0;
+            int cx = 0, cy = 0, cz = 0;
+            float lbf = 0.f;
+            if (t < ncell) {
+                const int c = t == 0 ? home : (t <= home ? t - 1 : t);
+                cx = x0 + c % nx; cy = y0 + (c / nx) % ny; cz = z0 + c / (nx * ny);
+                const double bd = box_d2(g, cx, cy, cz, cl, sx, sy, sz);
+                if (bd <= gbest * (1.0 + 1e-9) + 1e-12) {
+                    valid = grid_lookup(tab, tmask, l, morton3(cx, cy, cz), st, en);
+                    lbf = __double2float_rd(bd);
+                }
+            }
+            const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+            if (valid) {
+                const int pos = top + __popc(vm & ~((2u << gl) - 1u));
+                stk[pos] = make_uint4(st, en, (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20), (unsigned)l);
+                stk_lb[pos] = lbf;
+            }
+            top += __popc(vm);
         }
+        __syncwarp(gmask);
+        while (top > 0) {
+            if (++pops > kPopBudget) break;
+            --top;
+            const uint4 en4 = stk[top];
+            const float lbf = stk_lb[top];
+            __syncwarp(gmask);
+            if ((double)lbf > gbest * (1.0 + 1e-9) + 1e-12) continue;
+            const int el = (int)en4.w;
+            const unsigned cnt = en4.y - en4.x;
+            if (el == 0 || cnt <= (unsigned)kBigRun || top + 8 > kStack) {
+                for (unsigned p = en4.x + gl; p < en4.y; p += kG) {
+                    if constexpr (!TW) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(recs + p));
+                        const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (d2f <= thr) {
+                            const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                            const int idx = __float_as_int(v.w);
+                            if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; thr = screen_thr(d2, e); }
+                        }
+                    } else {
+                        double x, y, z;
+                        int idx;
+                        load_rec(recs + p, x, y, z, idx);
+                        const double d2 = sqdist(sx, sy, sz, x, y, z);
+                        if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; }
+                    }
+                }
+                // share the bound: group-wide minimum of the lanes' best distances
+                double m = lb.d2;
+#pragma unroll
+                for (int o = kG / 2; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(gmask, m, o, kG));
+                if (m < gbest) { gbest = m; thr = fminf(thr, screen_thr(m, e)); }
+            } else {
+                // expand into the eight children, lane r <-> r-th nearest octant
+                const int cx = (int)(en4.z & 1023u), cy = (int)((en4.z >> 10) & 1023u), cz = (int)(en4.z >> 20);
+                const double pcl = g.c0 * (double)(1 << el), h = 0.5 * pcl;
+                const unsigned near = ((sx >= g.ox + cx * pcl + h) ? 4u : 0u) | ((sy >= g.oy + cy * pcl + h) ? 2u : 0u) |
+                                      ((sz >= g.oz + cz * pcl + h) ? 1u : 0u);
+                const unsigned child = near ^ ((0x76534210u >> (4 * gl)) & 7u);      // 0,1,2,4,3,5,6,7 axis flips
+                const int ccx = 2 * cx + (int)((child >> 2) & 1u), ccy = 2 * cy + (int)((child >> 1) & 1u), ccz = 2 * cz + (int)(child & 1u);
+                const double bd = box_d2(g, ccx, ccy, ccz, h, sx, sy, sz);
+                bool valid = false;
+                unsigned st = 0, en = 0;
+                if (bd <= gbest * (1.0 + 1e-9) + 1e-12) valid = grid_lookup(tab, tmask, el - 1, morton3(ccx, ccy, ccz), st, en);
+                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+                if (valid) {
+                    const int pos = top + __popc(vm & ~((2u << gl) - 1u));
+                    stk[pos] = make_uint4(st, en, (unsigned)ccx | ((unsigned)ccy << 10) | ((unsigned)ccz << 20), (unsigned)(el - 1));
+                    stk_lb[pos] = __double2float_rd(bd);
+                }
+                top += __popc(vm);
+                __syncwarp(gmask);
+            }
+        }
+        if (pops > kPopBudget) { heavy = true; break; }
         // every point within min(best radius, cl) has been seen: exact as soon as the best lies within cl
-        if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) return;
+        if (sqrt(gbest) * (1.0 + 1e-9) + 1e-12 <= cl) break;
+    }
+    // lexicographic (d2, index) minimum over the group; lanes that found nothing carry the incoming bound with pos = -1
+#pragma unroll
+    for (int o = kG / 2; o > 0; o >>= 1) {
+        const double od2 = __shfl_xor_sync(gmask, lb.d2, o, kG);
+        const int oidx = __shfl_xor_sync(gmask, lb.idx, o, kG);
+        const int opos = __shfl_xor_sync(gmask, lb.pos, o, kG);
+        if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
+    }
+    return heavy;
+}
+
+// Block-wide exact search for one deferred query: every cell of the level with edge >= bound/2 that touches the
+// ball of the current bound is looked up in parallel (one thread per cell) and the runs are scanned by whole warps
+// with float32 screening - a few microseconds even when the ball covers most of the scan.
+template <bool TW>
+__device__ __forceinline__ void block_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, Best& lb,
+                                             uint2* __restrict__ s_runs, int* __restrict__ s_nruns) {
+    typedef typename RecT<TW>::type Rec;
+    const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
+    const GridSpec g = tgt.grid;
+    const double br = sqrt(in_d2) * (1.0 + 1e-9) + 1e-12;
+    int l = 0;
+    while (l < g.top_level && g.c0 * (double)(1 << l) < 0.5 * br) ++l;
+    const double cl = g.c0 * (double)(1 << l);
+    const int x0 = cell_coord(sx - br, g.ox, g.inv_c0) >> l, x1 = cell_coord(sx + br, g.ox, g.inv_c0) >> l;
+    const int y0 = cell_coord(sy - br, g.oy, g.inv_c0) >> l, y1 = cell_coord(sy + br, g.oy, g.inv_c0) >> l;
+    const int z0 = cell_coord(sz - br, g.oz, g.inv_c0) >> l, z1 = cell_coord(sz + br, g.oz, g.inv_c0) >> l;
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
+    if (threadIdx.x == 0) *s_nruns = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncell; t += kIcpBlock) {
+        const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
+        if (box_d2(g, cx, cy, cz, cl, sx, sy, sz) > in_d2 * (1.0 + 1e-9) + 1e-12) continue;
+        unsigned st, en;
+        if (grid_lookup(tgt.table, tgt.table_mask, l, morton3(cx, cy, cz), st, en)) {
+            const int slot = atomicAdd(s_nruns, 1);
+            if (slot < kMaxRuns) s_runs[slot] = make_uint2(st, en);
+        }
+    }
+    __syncthreads();
+    const int nruns = min(*s_nruns, kMaxRuns);       // the host sizes levels so that ncell <= kMaxRuns
+    const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
+    const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
+    float thr = screen_thr(in_d2, e);
+    lb.d2 = in_d2; lb.idx = in_idx; lb.pos = -1;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    for (int rr = w; rr < nruns; rr += kIcpBlock / 32) {
+        const uint2 run = s_runs[rr];
+        for (unsigned p = run.x + lane; p < run.y; p += 32) {
+            if constexpr (!TW) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(recs + p));
+                const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (d2f <= thr) {
+                    const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                    const int idx = __float_as_int(v.w);
+                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; thr = screen_thr(d2, e); }
+                }
+            } else {
+                double x, y, z;
+                int idx;
+                load_rec(recs + p, x, y, z, idx);
+                const double d2 = sqdist(sx, sy, sz, x, y, z);
+                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; }
+            }
+        }
+        // tighten the screen with the warp's best
+        float wt = thr;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wt = fminf(wt, __shfl_xor_sync(kFull, wt, o));
+        thr = wt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od2 = __shfl_xor_sync(kFull, lb.d2, o);
+        const int oidx = __shfl_xor_sync(kFull, lb.idx, o);
+        const int opos = __shfl_xor_sync(kFull, lb.pos, o);
+        if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
     }
 }
 
@@ -272,23 +417,32 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
     if (threadIdx.x < 16) s_T[threadIdx.x] = st->T[threadIdx.x];
     __syncthreads();
 
+    __shared__ float4 s_stage[kGroupsPerBlock][kStage];
+    __shared__ int s_spos[kGroupsPerBlock][kStage];
+    __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
+    __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
+
+    const long long tk0 = clock64();
     double acc[kNS];
 #pragma unroll
     for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
 
     const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+    // ---- per lane: transform the source point, bound the search with the previous pass' match
+    double sx = 0, sy = 0, sz = 0;
+    int sidx = 0, level = 0;
+    bool active = false, heavy = false;
+    Best b;
+    b.d2 = ip.max_d2; b.idx = -1; b.pos = -1;
     if (i < n) {
         double px, py, pz;
-        int sidx;
         load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
-        const double sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
-        const double sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
-        const double sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
-        Best b;
-        b.d2 = ip.max_d2; b.idx = -1; b.pos = -1;
+        sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
+        sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
+        sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
         const GridSpec& g = tgt.grid;
-        int level = min(g.cold_level, g.top_level);
-        const bool finite = sx == sx && sy == sy && sz == sz;
+        level = 0;
+        active = (sx == sx && sy == sy && sz == sz) && ip.max_d2 > 0;
         if (pass > 0) {
             const int pv = pr.prev[i];
             if (pv >= 0) {
@@ -297,7 +451,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pv, x, y, z, idx);
                 const double d2 = sqdist(sx, sy, sz, x, y, z);
                 if (d2 < b.d2) {
-                    // the previous match bounds the search ball; accept it unless something is strictly better
+                    // the previous match bounds the search ball; it stays unless something is strictly better
                     b.d2 = d2; b.idx = idx; b.pos = pv;
                     const double br = sqrt(d2) * (1.0 + 1e-9) + 1e-12;
                     level = 0;
@@ -305,7 +459,186 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 }
             }
         }
-        if (finite && ip.max_d2 > 0) nn_search<TW>(tgt, sx, sy, sz, b, level);
+    }
+    // ---- union phase: the kG queries of a group are consecutive points of the Morton-sorted source, i.e. spatial
+    // neighbours.  At the two finest levels their search balls share cells, so the group looks the union of the cells
+    // up once and every lane screens every staged record against its own query: no per-query set-up, no divergence
+    // (all lanes walk the same runs) and broadcast loads.  A lane is done when its best lies within the level's edge.
+    const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
+    const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
+    const long long tk1 = clock64();
+    bool certified = !active;
+    unsigned long long dbg_cand = 0;
+    int dbg_c0 = 0, dbg_c1 = 0, dbg_fb = 0, dbg_cells = 0;
+    long long tu_look = 0, tu_scan = 0, tu_bbox = 0;
+    {
+        const GridSpec g = tgt.grid;
+        const TRec* __restrict__ trecs = reinterpret_cast<const TRec*>(tgt.recs);
+        uint2* runs = reinterpret_cast<uint2*>(s_stk[grp]);          // kStack * 16 bytes = 2 * kStack runs
+        const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
+        const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
+        float thr = screen_thr(b.d2, e);
+        const int gshift = lane & ~(kG - 1);
+        for (int lu = 0; lu <= min(kUnionLevels - 1, g.top_level); ++lu) {
+            const bool want = active && !certified && level <= lu;
+            if (!__any_sync(gmask, want)) continue;
+            const long long ta = clock64();
+            const double cl = g.c0 * (double)(1 << lu);
+            const double r = fmin((double)(sqrtf(__double2float_ru(b.d2)) * (1.0f + 1e-6f)) + 1e-12, cl);
+            int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1, z0 = 1 << 30, z1 = -1;
+            if (want) {
+                x0 = cell_coord(sx - r, g.ox, g.inv_c0) >> lu; x1 = cell_coord(sx + r, g.ox, g.inv_c0) >> lu;
+                y0 = cell_coord(sy - r, g.oy, g.inv_c0) >> lu; y1 = cell_coord(sy + r, g.oy, g.inv_c0) >> lu;
+                z0 = cell_coord(sz - r, g.oz, g.inv_c0) >> lu; z1 = cell_coord(sz + r, g.oz, g.inv_c0) >> lu;
+            }
+#pragma unroll
+            for (int o = kG / 2; o > 0; o >>= 1) {
+                x0 = min(x0, __shfl_xor_sync(gmask, x0, o, kG)); x1 = max(x1, __shfl_xor_sync(gmask, x1, o, kG));
+                y0 = min(y0, __shfl_xor_sync(gmask, y0, o, kG)); y1 = max(y1, __shfl_xor_sync(gmask, y1, o, kG));
+                z0 = min(z0, __shfl_xor_sync(gmask, z0, o, kG)); z1 = max(z1, __shfl_xor_sync(gmask, z1, o, kG));
+            }
+            const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
+            const long long tb = clock64();
+            tu_bbox += tb - ta;
+            if (ncell > kUnionMax) break;            // the group straddles a jump of the space-filling curve: serve lanes one by one
+            int nr = 0;
+            for (int base = 0; base < ncell; base += kG) {
+                const int t = base + gl;
+                bool valid = false;
+                unsigned st = 0, en = 0;
+                if (t < ncell) {
+                    const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
+                    valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(cx, cy, cz), st, en);
+                }
+                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+                if (valid) runs[nr + __popc(vm & ((1u << gl) - 1u))] = make_uint2(st, en);
+                nr += __popc(vm);
+            }
+            __syncwarp(gmask);
+            const long long tc = clock64();
+            tu_look += tc - tb;
+            if constexpr (!TW) {
+                // stage the union's records in shared memory, kStage at a time: every lane fetches different records
+                // (coalesced, many loads in flight), then all lanes screen the staged records against their own query
+                float4* stage = s_stage[grp];
+                int* spos = s_spos[grp];
+                int rr = 0;
+                unsigned off = 0;
+                while (rr < nr) {
+                    int fill = 0;
+                    while (rr < nr && fill < kStage) {
+                        const uint2 run = runs[rr];
+                        const unsigned len = min(run.y - run.x - off, (unsigned)(kStage - fill));
+                        for (unsigned q = gl; q < len; q += kG) {
+                            stage[fill + q] = __ldg(reinterpret_cast<const float4*>(trecs + run.x + off + q));
+                            spos[fill + q] = (int)(run.x + off + q);
+                        }
+                        fill += (int)len;
+                        off += len;
+                        if (run.x + off >= run.y) { ++rr; off = 0; }
+                    }
+                    if (lu == 0) dbg_cand += (gl == 0) ? fill : 0; else dbg_cells += (gl == 0) ? fill : 0;
+                    __syncwarp(gmask);
+#pragma unroll 8
+                    for (int j = 0; j < fill; ++j) {
+                        const float4 v = stage[j];
+                        const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (want && d2f <= thr) {
+                            const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                            const int idx = __float_as_int(v.w);
+                            if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = spos[j]; thr = screen_thr(d2, e); }
+                        }
+                    }
+                    __syncwarp(gmask);
+                }
+            } else {
+                for (int rr = 0; rr < nr; ++rr) {
+                    const uint2 run = runs[rr];
+                    for (unsigned p = run.x; p < run.y; ++p) {
+                        double x, y, z;
+                        int idx;
+                        load_rec(trecs + p, x, y, z, idx);
+                        const double d2 = sqdist(sx, sy, sz, x, y, z);
+                        if (want && (d2 < b.d2 || (d2 == b.d2 && idx < b.idx))) { b.d2 = d2; b.idx = idx; b.pos = (int)p; }
+                    }
+                }
+            }
+            __syncwarp(gmask);
+            tu_scan += clock64() - tc;
+            if (want) {
+                // every target point within min(previous bound, cl) of this lane's query was screened
+                if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) { certified = true; if (lu == 0) ++dbg_c0; else ++dbg_c1; }
+                else level = lu + 1;
+            }
+        }
+    }
+    const long long tk2 = clock64();
+    // ---- remaining queries (nearest neighbour beyond the union levels): kG lanes serve them one after the other
+    {
+        for (int k = 0; k < kG; ++k) {
+            const bool qa = __shfl_sync(gmask, (int)(active && !certified), k, kG) != 0;
+            if (!qa) continue;
+            if (gl == k) ++dbg_fb;
+            const double qx = __shfl_sync(gmask, sx, k, kG), qy = __shfl_sync(gmask, sy, k, kG), qz = __shfl_sync(gmask, sz, k, kG);
+            const double qd2 = __shfl_sync(gmask, b.d2, k, kG);
+            const int qidx = __shfl_sync(gmask, b.idx, k, kG), ql = __shfl_sync(gmask, level, k, kG);
+            Best lb;
+            const bool hv = group_search<TW>(tgt, qx, qy, qz, qd2, qidx, ql, ip.defer_level, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
+            if (gl == k) {
+                if (lb.pos >= 0) b = lb;
+                heavy = hv;
+            }
+        }
+    }
+    const long long tk3 = clock64();
+    if (ip.debug) {
+        const unsigned long long c0 = warp_sum(dbg_c0), c1 = warp_sum(dbg_c1), fb = warp_sum(dbg_fb), hv = warp_sum(heavy ? 1 : 0),
+                                 ce = warp_sum(dbg_cells), ac = warp_sum(active ? 1 : 0);
+        unsigned long long cand = dbg_cand;
+        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(kFull, cand, o);
+        if (lane == 0) {
+            atomicAdd(&st->dbg[0], cand); atomicAdd(&st->dbg[1], c0); atomicAdd(&st->dbg[2], c1); atomicAdd(&st->dbg[3], fb);
+            atomicAdd(&st->dbg[4], hv); atomicAdd(&st->dbg[5], ce); atomicAdd(&st->dbg[6], ac);
+        }
+    }
+    // ---- deferred (far) queries: the whole block serves them one at a time
+    {
+        __shared__ int s_nheavy, s_nruns;
+        __shared__ unsigned char s_hlist[kIcpBlock];
+        __shared__ uint2 s_runs[kMaxRuns];
+        __shared__ double s_q[4];
+        __shared__ int s_qi;
+        __shared__ double s_wd2[kIcpBlock / 32];
+        __shared__ int s_widx[kIcpBlock / 32], s_wpos[kIcpBlock / 32];
+        if (threadIdx.x == 0) s_nheavy = 0;
+        __syncthreads();
+        if (heavy) s_hlist[atomicAdd(&s_nheavy, 1)] = (unsigned char)threadIdx.x;
+        __syncthreads();
+        const int nheavy = s_nheavy;
+        for (int h = 0; h < nheavy; ++h) {
+            const int owner = s_hlist[h];
+            if ((int)threadIdx.x == owner) { s_q[0] = sx; s_q[1] = sy; s_q[2] = sz; s_q[3] = b.d2; s_qi = b.idx; }
+            __syncthreads();
+            Best lb;
+            block_search<TW>(tgt, s_q[0], s_q[1], s_q[2], s_q[3], s_qi, lb, s_runs, &s_nruns);
+            const int w = threadIdx.x >> 5;
+            if (lane == 0) { s_wd2[w] = lb.d2; s_widx[w] = lb.idx; s_wpos[w] = lb.pos; }
+            __syncthreads();
+            if ((int)threadIdx.x == owner) {
+                Best r = b;
+                int rpos = -1;
+                for (int ww = 0; ww < kIcpBlock / 32; ++ww)
+                    if (s_wpos[ww] >= 0 && (s_wd2[ww] < r.d2 || (s_wd2[ww] == r.d2 && s_widx[ww] < r.idx))) {
+                        r.d2 = s_wd2[ww]; r.idx = s_widx[ww]; rpos = s_wpos[ww];
+                    }
+                if (rpos >= 0) { r.pos = rpos; b = r; }
+            }
+            __syncthreads();
+        }
+    }
+    const long long tk4 = clock64();
+    if (i < n) {
         pr.prev[i] = b.pos;
         if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = b.pos >= 0 ? b.idx : -1;
         if (b.pos >= 0) {
@@ -334,7 +667,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
         }
     }
     // warp -> block reduction in a fixed order (bit-reproducible run to run)
-    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         if (METHOD == 0 && k >= 15 && k < 27) continue;
@@ -353,6 +686,13 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        const long long tk5 = clock64();
+        if (ip.debug) {
+        atomicAdd(&st->tl[0], (unsigned long long)(tk1 - tk0)); atomicAdd(&st->tl[1], (unsigned long long)(tk2 - tk1));
+        atomicAdd(&st->tl[2], (unsigned long long)(tk3 - tk2)); atomicAdd(&st->tl[3], (unsigned long long)(tk4 - tk3));
+        atomicAdd(&st->tl[4], (unsigned long long)(tk5 - tk4)); atomicAdd(&st->tl[5], 1ull);
+        atomicAdd(&st->dbg[7], (unsigned long long)tu_scan); atomicAdd(&st->tl[7], (unsigned long long)tu_look);
+        }
         const unsigned t = atomicAdd(&st->ticket, 1u);
         s_last = (t == (unsigned)nblk - 1u) ? 1 : 0;
     }
@@ -393,17 +733,29 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             st->updates = st->updates + 1;
         }
         st->err = src.counts[CNT_ERR] | tgt.counts[CNT_ERR];
+        if (ip.debug) atomicAdd(&st->tl[6], (unsigned long long)(clock64() - tk0));
         st->ticket = 0u;
         __threadfence();
     }
 }
 
+static const char* pass_name(int pass) {   // "icp_pass_00" ... so that the profile report separates the passes
+    static char names[64][16];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 64; ++i) snprintf(names[i], sizeof(names[i]), "icp_pass_%02d", i);
+        init = true;
+    }
+    return names[pass < 63 ? pass : 63];
+}
+
 template <int METHOD>
 static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, const IcpParams& ip, int pass, int combos_mask) {
-    if (combos_mask & 1) L.launch("icp_pass", k_icp_pass<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch("icp_pass", k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch("icp_pass", k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch("icp_pass", k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    const char* nm = pass_name(pass);
+    if (combos_mask & 1) L.launch(nm, k_icp_pass<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 2) L.launch(nm, k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 4) L.launch(nm, k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 8) L.launch(nm, k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
 }
 
 // combos_mask bit (2*src_wide + tgt_wide) set when some pair of the batch has that record-type combination

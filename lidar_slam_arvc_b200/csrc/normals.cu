@@ -112,15 +112,52 @@ constexpr int kBins = 512;
 constexpr int kCand = 128;
 constexpr int kCanon = 320;          // most neighbours the canonical (sorted, sequential) re-summation handles
 // per-warp shared memory, two layouts that are never live at the same time:
-//   selection : int hist[kBins] | double cand_d2[kCand] | int cand_idx[kCand]
+//   selection : int hist[kBins] | double cand_d2[kCand] | int cand_idx[kCand] | int cand_pos[kCand]
 //   canonical : double key_d2[kCanon] | int key_idx[kCanon] | int key_pos[kCanon] | int order[kCanon]
 constexpr int kWarpSmem = kCanon * 20;
-static_assert(kBins * 4 + kCand * 12 <= kWarpSmem, "selection layout must fit");
+static_assert(kBins * 4 + kCand * 16 <= kWarpSmem, "selection layout must fit");
 constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
 
 __device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
 }  // namespace
+
+// One candidate record, evaluated lazily: a float32 distance classifies most candidates (narrow records are exact
+// float32 values, so d2f = d2 * (1 + theta), |theta| < 1e-6); the float64 distance - bit-equal to the oracle's -
+// is only computed for candidates that are used or that sit within that error of a decision boundary.
+template <bool WIDE> struct CandEval;
+
+template <> struct CandEval<false> {
+    float4 v;
+    float d2f;
+    __device__ __forceinline__ void load(const RecF* recs, unsigned j, float qxf, float qyf, float qzf, double, double, double) {
+        v = __ldg(reinterpret_cast<const float4*>(recs + j));
+        const float dx = qxf - v.x, dy = qyf - v.y, dz = qzf - v.z;
+        d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    }
+    __device__ __forceinline__ double exact(double qx, double qy, double qz) const { return sqdist(qx, qy, qz, (double)v.x, (double)v.y, (double)v.z); }
+    __device__ __forceinline__ double x() const { return (double)v.x; }
+    __device__ __forceinline__ double y() const { return (double)v.y; }
+    __device__ __forceinline__ double z() const { return (double)v.z; }
+    __device__ __forceinline__ int idx() const { return __float_as_int(v.w); }
+    // -1: certainly d2 >= bound, +1: certainly d2 < bound, 0: too close to call in float32
+    __device__ __forceinline__ int below(float lo, float hi) const { return d2f > hi ? -1 : (d2f < lo ? 1 : 0); }
+};
+
+template <> struct CandEval<true> {
+    double px, py, pz, d2;
+    int id;
+    __device__ __forceinline__ void load(const RecD* recs, unsigned j, float, float, float, double qx, double qy, double qz) {
+        load_rec(recs + j, px, py, pz, id);
+        d2 = sqdist(qx, qy, qz, px, py, pz);
+    }
+    __device__ __forceinline__ double exact(double, double, double) const { return d2; }
+    __device__ __forceinline__ double x() const { return px; }
+    __device__ __forceinline__ double y() const { return py; }
+    __device__ __forceinline__ double z() const { return pz; }
+    __device__ __forceinline__ int idx() const { return id; }
+    __device__ __forceinline__ int below(float, float) const { return 0; }
+};
 
 template <bool WIDE>
 __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np) {
@@ -136,10 +173,12 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     double qx, qy, qz;
     int qidx;
     load_rec(recs + p, qx, qy, qz, qidx);
+    const float qxf = (float)qx, qyf = (float)qy, qzf = (float)qz;
 
     const GridSpec g = s.grid;
     const int L = np.level;
     const double r2 = np.radius * np.radius;
+    const float r2_lo = (float)(r2 * (1.0 - 2e-6)), r2_hi = (float)(r2 * (1.0 + 2e-6));
     const double rinf = np.radius * (1.0 + 1e-9) + 1e-12;
     const double cl = g.c0 * (double)(1 << L);
     const int x0 = cell_coord(qx - rinf, g.ox, g.inv_c0) >> L, x1 = cell_coord(qx + rinf, g.ox, g.inv_c0) >> L;
@@ -152,10 +191,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     int* hist = reinterpret_cast<int*>(wmem);
     double* cand_d2 = reinterpret_cast<double*>(wmem + kBins * 4);
     int* cand_idx = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 8);
-    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    int cnt = 0;
-    double tau_d2 = r2;      // inclusion: d2 < r2 and (d2, idx) <= (tau_d2, tau_idx)
-    int tau_idx = 0x7fffffff;
+    int* cand_pos = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 12);
 
     // look the (<= 27) cells up once: lane c owns cell c; cells whose box misses the ball are skipped
     unsigned st = 0, en = 0;
@@ -169,67 +205,57 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
             grid_lookup(s.table, s.table_mask, L, morton3(cx, cy, cz), st, en);
     }
     const int total = warp_sum((int)(en - st));
-    const bool need_select = total > np.max_nn;
 
-    int bstar = -1, need = 0;
+    // d2 -> bucket, monotone in the exact d2; the float32 shortcut is taken only when it cannot cross a bucket edge
     const double bin_scale = (double)kBins / r2;
-    for (int phase = need_select ? 1 : 3; phase <= 3; ++phase) {
-        if (phase == 1) {
-            for (int b = lane; b < kBins; b += 32) hist[b] = 0;
-            __syncwarp();
+    const float bin_scale_f = (float)bin_scale;
+    auto bucket = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> int {
+        if constexpr (!WIDE) {
+            const float u = c.d2f * bin_scale_f;
+            const int b = (int)u;
+            const float fr = u - (float)b;
+            if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) return b;
         }
-        int ncand = 0;
-        {
-            for (int cc = 0; cc < ncell; ++cc) {
-                const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-                for (unsigned t = cst; t < cen; t += 32) {
-                    const unsigned j = t + lane;
-                    double x = 0, y = 0, z = 0, d2 = INFINITY;
-                    int idx = 0;
-                    if (j < cen) {
-                        load_rec(recs + j, x, y, z, idx);
-                        d2 = sqdist(qx, qy, qz, x, y, z);
-                    }
-                    const bool in = d2 < r2;
-                    if (phase == 1) {
-                        if (in) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
-                    } else if (phase == 2) {
-                        const bool hit = in && min(kBins - 1, (int)(d2 * bin_scale)) == bstar;
-                        const unsigned m = __ballot_sync(kFull, hit);
-                        if (hit) {
-                            const int slot = ncand + __popc(m & ((1u << lane) - 1u));
-                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = idx; }
-                        }
-                        ncand += __popc(m);
-                    } else {
-                        if (in && !key_less(tau_d2, tau_idx, d2, idx)) {
-                            const double ux = x - qx, uy = y - qy, uz = z - qz;
-                            sx += ux; sy += uy; sz += uz;
-                            sxx = fma(ux, ux, sxx); sxy = fma(ux, uy, sxy); sxz = fma(ux, uz, sxz);
-                            syy = fma(uy, uy, syy); syz = fma(uy, uz, syz); szz = fma(uz, uz, szz);
-                            ++cnt;
-                        }
-                    }
-                }
+        if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
+        return min(kBins - 1, (int)(d2 * bin_scale));
+    };
+    // membership in the radius, exact
+    auto in_radius = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> bool {
+        const int t = c.below(r2_lo, r2_hi);
+        if (t != 0) return t > 0;
+        if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
+        return d2 < r2;
+    };
+
+    int bstar = kBins, need = 0;       // buckets < bstar are taken whole; `need` more come from bucket bstar
+    if (total > np.max_nn) {
+        // ---- pass A: bucket histogram of the in-radius candidates
+        for (int b = lane; b < kBins; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (int cc = 0; cc < ncell; ++cc) {
+            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+            for (unsigned j = cst + lane; j < cen; j += 32) {
+                CandEval<WIDE> c;
+                c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                double d2 = 0;
+                bool have = false;
+                if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
             }
         }
-        if (phase == 1) {
-            __syncwarp();
-            // locate the bucket holding the max_nn-th neighbour: lane owns kBins/32 consecutive buckets
-            constexpr int per = kBins / 32;
-            int local = 0;
+        __syncwarp();
+        constexpr int per = kBins / 32;      // lane owns `per` consecutive buckets
+        int local = 0;
 #pragma unroll
-            for (int b = 0; b < per; ++b) local += hist[lane * per + b];
-            int inc = local;
+        for (int b = 0; b < per; ++b) local += hist[lane * per + b];
+        int inc = local;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += t;
-            }
-            const int n_in = __shfl_sync(kFull, inc, 31);
-            if (n_in <= np.max_nn) { phase = 2; continue; }          // everything in radius is used: go to phase 3
-            int before = inc - local;
-            int myb = -1, myneed = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int n_in = __shfl_sync(kFull, inc, 31);
+        if (n_in > np.max_nn) {
+            int before = inc - local, myb = -1, myneed = 0;
             if (before < np.max_nn && inc >= np.max_nn) {
 #pragma unroll
                 for (int b = 0; b < per; ++b) {
@@ -242,53 +268,111 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
             const int src_lane = __ffs(who) - 1;
             bstar = __shfl_sync(kFull, myb, src_lane);
             need = __shfl_sync(kFull, myneed, src_lane);
-        } else if (phase == 2) {
-            __syncwarp();
-            if (ncand <= kCand) {
-                // exact rank inside the boundary bucket
-                double td2 = 0;
-                int tidx = 0;
+        }
+        __syncwarp();
+    }
+
+    // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    int cnt = 0, ncand = 0;
+    double tau_d2 = r2;      // selected <=> d2 < r2 and (d2, idx) <= (tau_d2, tau_idx)
+    int tau_idx = 0x7fffffff;
+    auto accumulate = [&](double x, double y, double z) {
+        const double ux = x - qx, uy = y - qy, uz = z - qz;      // centred: exact differences of float32 payloads
+        sx += ux; sy += uy; sz += uz;
+        sxx = fma(ux, ux, sxx); sxy = fma(ux, uy, sxy); sxz = fma(ux, uz, sxz);
+        syy = fma(uy, uy, syy); syz = fma(uy, uz, syz); szz = fma(uz, uz, szz);
+        ++cnt;
+    };
+    for (int cc = 0; cc < ncell; ++cc) {
+        const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+        for (unsigned t = cst; t < cen; t += 32) {
+            const unsigned j = t + lane;
+            bool hit = false;
+            double d2 = 0;
+            CandEval<WIDE> c;
+            if (j < cen) {
+                c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
                 bool have = false;
-                for (int a = lane; a < ncand; a += 32) {
-                    const double d2a = cand_d2[a];
-                    const int ia = cand_idx[a];
-                    int rank = 0;
-                    for (int b = 0; b < ncand; ++b) rank += key_less(cand_d2[b], cand_idx[b], d2a, ia) ? 1 : 0;
-                    if (rank == need - 1) { td2 = d2a; tidx = ia; have = true; }
+                if (in_radius(c, d2, have)) {
+                    const int b = bstar == kBins ? 0 : bucket(c, d2, have);
+                    if (b < bstar) accumulate(c.x(), c.y(), c.z());
+                    else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
                 }
-                const unsigned who = __ballot_sync(kFull, have);
-                const int src_lane = __ffs(who) - 1;
-                tau_d2 = __shfl_sync(kFull, td2, src_lane);
-                tau_idx = __shfl_sync(kFull, tidx, src_lane);
-            } else {
-                // pathological bucket (duplicates): extract the `need` smallest keys one at a time
-                double last_d2 = -1.0;
-                int last_idx = -1;
-                for (int t = 0; t < need; ++t) {
-                    double md2 = INFINITY;
-                    int midx = 0x7fffffff;
-                    {
-                        for (int cc = 0; cc < ncell; ++cc) {
-                            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-                            for (unsigned u = cst + lane; u < cen; u += 32) {
-                                double x, y, z;
-                                int idx;
-                                load_rec(recs + u, x, y, z, idx);
-                                const double d2 = sqdist(qx, qy, qz, x, y, z);
-                                if (d2 < r2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
-                                    key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
-                            }
-                        }
+            }
+            if (bstar != kBins) {
+                const unsigned m = __ballot_sync(kFull, hit);
+                if (hit) {
+                    const int slot = ncand + __popc(m & ((1u << lane) - 1u));
+                    if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                }
+                ncand += __popc(m);
+            }
+        }
+    }
+    if (bstar != kBins) {
+        __syncwarp();
+        if (ncand <= kCand) {
+            // exact rank inside the boundary bucket; the `need` smallest (d2, index) keys join the neighbourhood
+            double td2 = 0;
+            int tidx = 0;
+            bool have_tau = false;
+            for (int a = lane; a < ncand; a += 32) {
+                const double d2a = cand_d2[a];
+                const int ia = cand_idx[a];
+                int rank = 0;
+                for (int b = 0; b < ncand; ++b) rank += key_less(cand_d2[b], cand_idx[b], d2a, ia) ? 1 : 0;
+                if (rank < need) {
+                    double x, y, z;
+                    int idx;
+                    load_rec(recs + cand_pos[a], x, y, z, idx);
+                    accumulate(x, y, z);
+                }
+                if (rank == need - 1) { td2 = d2a; tidx = ia; have_tau = true; }
+            }
+            const unsigned who = __ballot_sync(kFull, have_tau);
+            const int src_lane = __ffs(who) - 1;
+            tau_d2 = __shfl_sync(kFull, td2, src_lane);
+            tau_idx = __shfl_sync(kFull, tidx, src_lane);
+        } else {
+            // pathological bucket (many duplicates): extract the `need` smallest keys of the bucket one at a time ...
+            double last_d2 = -1.0;
+            int last_idx = -1;
+            for (int t = 0; t < need; ++t) {
+                double md2 = INFINITY;
+                int midx = 0x7fffffff;
+                for (int cc = 0; cc < ncell; ++cc) {
+                    const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+                    for (unsigned u = cst + lane; u < cen; u += 32) {
+                        double x, y, z;
+                        int idx;
+                        load_rec(recs + u, x, y, z, idx);
+                        const double d2 = sqdist(qx, qy, qz, x, y, z);
+                        if (d2 < r2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
+                            key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
                     }
+                }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double od2 = __shfl_xor_sync(kFull, md2, o);
-                        const int oidx = __shfl_xor_sync(kFull, midx, o);
-                        if (key_less(od2, oidx, md2, midx)) { md2 = od2; midx = oidx; }
-                    }
-                    last_d2 = md2; last_idx = midx;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od2 = __shfl_xor_sync(kFull, md2, o);
+                    const int oidx = __shfl_xor_sync(kFull, midx, o);
+                    if (key_less(od2, oidx, md2, midx)) { md2 = od2; midx = oidx; }
                 }
-                tau_d2 = last_d2; tau_idx = last_idx;
+                last_d2 = md2; last_idx = midx;
+            }
+            tau_d2 = last_d2; tau_idx = last_idx;
+            // ... and redo the accumulation with the exact threshold
+            sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0;
+            cnt = 0;
+            for (int cc = 0; cc < ncell; ++cc) {
+                const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
+                for (unsigned u = cst + lane; u < cen; u += 32) {
+                    double x, y, z;
+                    int idx;
+                    load_rec(recs + u, x, y, z, idx);
+                    const double d2 = sqdist(qx, qy, qz, x, y, z);
+                    if (d2 < r2 && !key_less(tau_d2, tau_idx, d2, idx)) accumulate(x, y, z);
+                }
             }
         }
     }
