@@ -269,7 +269,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
     e2e_value = world * P * args.steps / float(t_s.item())
-    d2h_bytes = int(432 * P + (160 * P * world if world > 1 else 0))   # PairState read-back (+ gathered records)
+    d2h_bytes = int(464 * P + (160 * P * world if world > 1 else 0))   # per-pair state read-back (+ gathered records)
 
     # ---- roofline of the dominant kernel (device events recorded around every launch of the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

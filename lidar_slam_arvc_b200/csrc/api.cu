@@ -1,6 +1,7 @@
 // C-ABI of the engine (include/arvc_icp.h): context, scan store, batch orchestration.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -558,14 +559,16 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
         std::vector<PairDev> hp(pass ? n_pairs : 0);
         for (int i = 0; i < n_pairs; ++i) {
             const size_t cap = (size_t)S[i]->dev.cap;
-            const size_t nblk = (cap + kIcpBlock - 1) / kIcpBlock;
-            double* partials = P.take<double>(nblk * kSumStride);
+            const size_t nrows = (cap + kIcpBlock - 1) / kIcpBlock * (kIcpBlock / 32);
+            double* partials = P.take<double>(nrows * kSumStride);
             int* prev = P.take<int>(cap);
+            float* lb2 = P.take<float>(cap);
+            unsigned char* cpass = P.take<unsigned char>(cap);
             int* ct = trace ? P.take<int>(cap * passes) : nullptr;
             double* stt = trace ? P.take<double>((size_t)passes * 18) : nullptr;
             if (pass) {
                 hp[i].src = S[i]->d_dev; hp[i].tgt = T[i]->d_dev; hp[i].state = d_states + i;
-                hp[i].partials = partials; hp[i].prev = prev; hp[i].corr_trace = ct; hp[i].state_trace = stt;
+                hp[i].partials = partials; hp[i].prev = prev; hp[i].lb2 = lb2; hp[i].cert_pass = cpass; hp[i].corr_trace = ct; hp[i].state_trace = stt;
                 if (trace && d_corr_trace) { *d_corr_trace = ct; *d_state_trace = stt; }
             }
         }
@@ -578,7 +581,10 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             pb.h_states = reinterpret_cast<PairState*>(ctx->pinned_get(sizeof(PairState) * n_pairs, &pb.h_bytes));
             if (!pb.h_states) return ctx->fail(ARVC_E_NOMEM, "icp: pinned host allocation failed");
             std::memset(pb.h_states, 0, sizeof(PairState) * n_pairs);
-            for (int i = 0; i < n_pairs; ++i) std::memcpy(pb.h_states[i].T, init_T + 16 * (size_t)i, sizeof(double) * 16);
+            for (int i = 0; i < n_pairs; ++i) {
+                std::memcpy(pb.h_states[i].T, init_T + 16 * (size_t)i, sizeof(double) * 16);
+                std::memcpy(pb.h_states[i].Thist, init_T + 16 * (size_t)i, sizeof(double) * 12);
+            }
             CK(cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
             CK(cudaMemcpyAsync(d_states, pb.h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
             IcpParams ip{};
@@ -586,12 +592,14 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             ip.max_d2 = p->max_corr_dist > 0 ? p->max_corr_dist * p->max_corr_dist : 0.0;
             ip.rel_fitness = p->rel_fitness; ip.rel_rmse = p->rel_rmse; ip.max_iter = p->max_iter; ip.method = p->method;
             {
-                const char* dl = getenv("ARVC_DEFER_LEVEL");   // tuning knob; results do not depend on it
-                ip.defer_level = dl ? atoi(dl) : kMortonBits;   // block-wide phase off by default (measured slower)
-                ip.debug = getenv("ARVC_DEBUG_STATS") ? 1 : 0;
+                const char* cm = getenv("ARVC_CERT_MARGIN");      // tuning knob; results do not depend on it
+                ip.cert_margin = cm ? atof(cm) : 0.02;
+                ip.debug = getenv("ARVC_DEBUG_STATS") ? atoi(getenv("ARVC_DEBUG_STATS")) : 0;
             }
             run_icp(ctx->L, d_pairs, n_pairs, src_cap_max, ip, combos);
-            CK(cudaMemcpyAsync(pb.h_states, d_states, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->L.stream));
+            static_assert(offsetof(PairState, Thist) == kPairStateHead, "PairState head layout");
+            CK(cudaMemcpy2DAsync(pb.h_states, sizeof(PairState), d_states, sizeof(PairState), kPairStateHead, n_pairs,
+                                 cudaMemcpyDeviceToHost, ctx->L.stream));
         }
     }
     if (src_cap_out) *src_cap_out = src_cap_max;
@@ -606,13 +614,11 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     int err = 0;
     if (getenv("ARVC_DEBUG_STATS")) {
-        unsigned long long tot[8] = {0}, tl[8] = {0};
+        unsigned long long tot[4] = {0};
         long long passes = 0;
-        for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 8; ++k) { tot[k] += pb.h_states[i].dbg[k]; tl[k] += pb.h_states[i].tl[k]; } passes += pb.h_states[i].passes; }
-        fprintf(stderr, "[arvc timeline] blocks=%llu avg cycles: prologue=%.0f union=%.0f fallback=%.0f heavy=%.0f epilogue=%.0f | last-block total avg=%.0f | union: lookup=%.0f scan=%.0f\n", tl[5],
-                (double)tl[0] / tl[5], (double)tl[1] / tl[5], (double)tl[2] / tl[5], (double)tl[3] / tl[5], (double)tl[4] / tl[5], (double)tl[6] / (passes ? passes : 1), (double)tl[7] / tl[5], (double)tot[7] / tl[5]);
-        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu union_cand_l0=%llu cert_l0=%llu cert_l1=%llu fallback=%llu heavy=%llu union_cand_l1=%llu\n",
-                pb.n_pairs, passes, tot[6], tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]);
+        for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 4; ++k) tot[k] += pb.h_states[i].dbg[k]; passes += pb.h_states[i].passes; }
+        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu skipped_by_certificate=%llu union=%llu fallback=%llu\n", pb.n_pairs, passes,
+                tot[3], tot[0], tot[1], tot[2]);
     }
     for (int i = 0; i < pb.n_pairs; ++i) {
         const PairState& st = pb.h_states[i];

@@ -47,6 +47,8 @@ struct Launcher {
 };
 
 // pair descriptor + state for the device-resident ICP iteration
+constexpr int kThist = 32;     // passes whose transformation is kept for the nearest-neighbour certificates
+
 struct __align__(16) PairState {
     double T[16];           // cumulative transformation used by the NEXT pass
     double fitness, rmse;   // of the last completed pass
@@ -55,19 +57,22 @@ struct __align__(16) PairState {
     int updates;            // executed updates
     int done;
     int ncorr;
-    unsigned ticket;
     int err;                // OR of the two scans' device error flags
-    int pad[2];
-    unsigned long long dbg[8];   // search statistics, accumulated over all passes
-    unsigned long long tl[8];    // per-phase clock cycles summed over blocks (debug timeline)
+    int pad[3];
+    unsigned long long dbg[4];   // search statistics (ARVC_DEBUG_STATS): skipped / union / fallback queries, queries
+    // ---- device-only tail (not copied back): top three rows of the transformation each pass was evaluated at
+    double Thist[12 * kThist];
 };
+constexpr size_t kPairStateHead = 16 * 8 + 2 * 8 + 32 * 8 + 8 * 4 + 4 * 8;   // bytes read back per pair
 
 struct PairDev {
     const ScanDev* src;
     const ScanDev* tgt;
     PairState* state;
-    double* partials;       // [nblk][kSumStride]
+    double* partials;       // [warps][kSumStride]
     int* prev;              // [src cap] Morton position of last pass' match in the target, or -1
+    float* lb2;             // [src cap] certificate: lower bound on the distance to every other target point ...
+    unsigned char* cert_pass;   // [src cap] ... at the pass it was established (255 = none)
     int* corr_trace;        // optional [(max_iter+1)][src cap] (cloud order), may be null
     double* state_trace;    // optional [(max_iter+1)][18]: T16, fitness, rmse
 };
@@ -76,14 +81,15 @@ struct IcpParams {
     double max_d2;          // max_corr_dist^2
     double max_d;
     double rel_fitness, rel_rmse;
+    double cert_margin;     // extra radius (m) the union phase covers so that later passes can skip the search
     int max_iter;
     int method;
-    int defer_level;        // coarsest grid level the 8-lane search handles itself (farther queries: block-wide phase)
-    int debug;              // collect search statistics / phase timeline into PairState (ARVC_DEBUG_STATS)
+    int debug;              // collect search statistics into PairState (ARVC_DEBUG_STATS)
+    int pad;
 };
 
 constexpr int kSumStride = 32;
-constexpr int kIcpBlock = 128;
+constexpr int kIcpBlock = 64;
 
 void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const FilterParams& fp, const VoxelParams& vp,
                     bool voxel_on);

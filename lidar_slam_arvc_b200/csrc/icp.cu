@@ -36,8 +36,6 @@ constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 2;  // finest levels served by the shared-candidate (union) phase
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
-constexpr int kPopBudget = 96;   // stack pops a group spends on one query before deferring it
-constexpr int kMaxRuns = 256;    // cells a deferred query may touch (6^3 = 216 at most)
 
 __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
     const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
@@ -55,8 +53,8 @@ __device__ __forceinline__ float screen_thr(double best_d2, float e) {
 }
 
 template <bool TW>
-__device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, int level,
-                                             int defer_level, Best& lb, uint4* __restrict__ stk, float* __restrict__ stk_lb, int gl,
+__device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, int level,
+                                             Best& lb, uint4* __restrict__ stk, float* __restrict__ stk_lb, int gl,
                                              unsigned gmask) {
     typedef typename RecT<TW>::type Rec;
     const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
@@ -69,13 +67,8 @@ __device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, doub
     double gbest = in_d2;                       // group-wide best d2 (every lane holds the same value)
     float thr = screen_thr(gbest, e);
     lb.d2 = in_d2; lb.idx = in_idx; lb.pos = -1;
-    bool heavy = false;
-    int pops = 0;
 
     for (int l = level; l <= g.top_level; ++l) {
-        // queries whose nearest neighbour is far (occlusion shadows) would walk hundreds of cells here, one
-        // dependent lookup after the other: hand them to the block-wide phase with the bound found so far
-        if (l > defer_level || pops > kPopBudget) { heavy = true; break; }
         const double cl = g.c0 * (double)(1 << l);
         const double br = sqrt(gbest) * (1.0 + 1e-9) + 1e-12;
         const double r = fmin(br, cl);
@@ -113,7 +106,6 @@ __device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, doub
         }
         __syncwarp(gmask);
         while (top > 0) {
-            if (++pops > kPopBudget) break;
             --top;
             const uint4 en4 = stk[top];
             const float lbf = stk_lb[top];
@@ -167,7 +159,6 @@ __device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, doub
                 __syncwarp(gmask);
             }
         }
-        if (pops > kPopBudget) { heavy = true; break; }
         // every point within min(best radius, cl) has been seen: exact as soon as the best lies within cl
         if (sqrt(gbest) * (1.0 + 1e-9) + 1e-12 <= cl) break;
     }
@@ -177,77 +168,6 @@ __device__ __forceinline__ bool group_search(const ScanDev& tgt, double sx, doub
         const double od2 = __shfl_xor_sync(gmask, lb.d2, o, kG);
         const int oidx = __shfl_xor_sync(gmask, lb.idx, o, kG);
         const int opos = __shfl_xor_sync(gmask, lb.pos, o, kG);
-        if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
-    }
-    return heavy;
-}
-
-// Block-wide exact search for one deferred query: every cell of the level with edge >= bound/2 that touches the
-// ball of the current bound is looked up in parallel (one thread per cell) and the runs are scanned by whole warps
-// with float32 screening - a few microseconds even when the ball covers most of the scan.
-template <bool TW>
-__device__ __forceinline__ void block_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, Best& lb,
-                                             uint2* __restrict__ s_runs, int* __restrict__ s_nruns) {
-    typedef typename RecT<TW>::type Rec;
-    const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(tgt.recs);
-    const GridSpec g = tgt.grid;
-    const double br = sqrt(in_d2) * (1.0 + 1e-9) + 1e-12;
-    int l = 0;
-    while (l < g.top_level && g.c0 * (double)(1 << l) < 0.5 * br) ++l;
-    const double cl = g.c0 * (double)(1 << l);
-    const int x0 = cell_coord(sx - br, g.ox, g.inv_c0) >> l, x1 = cell_coord(sx + br, g.ox, g.inv_c0) >> l;
-    const int y0 = cell_coord(sy - br, g.oy, g.inv_c0) >> l, y1 = cell_coord(sy + br, g.oy, g.inv_c0) >> l;
-    const int z0 = cell_coord(sz - br, g.oz, g.inv_c0) >> l, z1 = cell_coord(sz + br, g.oz, g.inv_c0) >> l;
-    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
-    if (threadIdx.x == 0) *s_nruns = 0;
-    __syncthreads();
-    for (int t = threadIdx.x; t < ncell; t += kIcpBlock) {
-        const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
-        if (box_d2(g, cx, cy, cz, cl, sx, sy, sz) > in_d2 * (1.0 + 1e-9) + 1e-12) continue;
-        unsigned st, en;
-        if (grid_lookup(tgt.table, tgt.table_mask, l, morton3(cx, cy, cz), st, en)) {
-            const int slot = atomicAdd(s_nruns, 1);
-            if (slot < kMaxRuns) s_runs[slot] = make_uint2(st, en);
-        }
-    }
-    __syncthreads();
-    const int nruns = min(*s_nruns, kMaxRuns);       // the host sizes levels so that ncell <= kMaxRuns
-    const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
-    const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
-    float thr = screen_thr(in_d2, e);
-    lb.d2 = in_d2; lb.idx = in_idx; lb.pos = -1;
-    const int lane = lane_id(), w = threadIdx.x >> 5;
-    for (int rr = w; rr < nruns; rr += kIcpBlock / 32) {
-        const uint2 run = s_runs[rr];
-        for (unsigned p = run.x + lane; p < run.y; p += 32) {
-            if constexpr (!TW) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(recs + p));
-                const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
-                const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (d2f <= thr) {
-                    const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
-                    const int idx = __float_as_int(v.w);
-                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; thr = screen_thr(d2, e); }
-                }
-            } else {
-                double x, y, z;
-                int idx;
-                load_rec(recs + p, x, y, z, idx);
-                const double d2 = sqdist(sx, sy, sz, x, y, z);
-                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; }
-            }
-        }
-        // tighten the screen with the warp's best
-        float wt = thr;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wt = fminf(wt, __shfl_xor_sync(kFull, wt, o));
-        thr = wt;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od2 = __shfl_xor_sync(kFull, lb.d2, o);
-        const int oidx = __shfl_xor_sync(kFull, lb.idx, o);
-        const int opos = __shfl_xor_sync(kFull, lb.pos, o);
         if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
     }
 }
@@ -397,53 +317,53 @@ __device__ void solve_update(int method, const double* S, double* upd) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// Pass kernel: one thread per source point (Morton order), kIcpBlock threads per block, no block-level barrier
+// after the prologue - warps are independent and write one row of partial sums each.
+// ---------------------------------------------------------------------------------------------------
 template <int METHOD, bool SW, bool TW>
 __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
-    __shared__ double s_T[16];
-    __shared__ double s_red[kIcpBlock / 32][kNS];
-    __shared__ int s_last;
-
-    const PairDev& pr = pairs[blockIdx.y];
-    const ScanDev& src = *pr.src;
-    const ScanDev& tgt = *pr.tgt;
-    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
-    PairState* st = pr.state;
-    if (st->done) return;
-    const int n = src.counts[CNT_NPTS];
-    const int nblk = max(1, (n + kIcpBlock - 1) / kIcpBlock);
-    if ((int)blockIdx.x >= nblk) return;
-    if (threadIdx.x < 16) s_T[threadIdx.x] = st->T[threadIdx.x];
-    __syncthreads();
-
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
     __shared__ int s_spos[kGroupsPerBlock][kStage];
     __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
     __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
 
-    const long long tk0 = clock64();
-    double acc[kNS];
+    const PairDev& pr = pairs[blockIdx.y];
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
+    const PairState* __restrict__ st = pr.state;
+    if (st->done) return;
+    const int n = src.counts[CNT_NPTS];
+    const int nblk = max(1, (n + kIcpBlock - 1) / kIcpBlock);
+    if ((int)blockIdx.x >= nblk) return;
+    const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
+    const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
+    double T[12];
 #pragma unroll
-    for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
+    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
 
     const int i = blockIdx.x * kIcpBlock + threadIdx.x;
     // ---- per lane: transform the source point, bound the search with the previous pass' match
     double sx = 0, sy = 0, sz = 0;
     int sidx = 0, level = 0;
-    bool active = false, heavy = false;
+    bool active = false, certified = true;
+    float cert_lb = 0.f;                 // new certificate (0 = none)
     Best b;
     b.d2 = ip.max_d2; b.idx = -1; b.pos = -1;
+    int stat_skip = 0, stat_union = 0, stat_fb = 0;
     if (i < n) {
         double px, py, pz;
         load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
-        sx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[3];
-        sy = s_T[4] * px + s_T[5] * py + s_T[6] * pz + s_T[7];
-        sz = s_T[8] * px + s_T[9] * py + s_T[10] * pz + s_T[11];
+        sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
+        sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+        sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
         const GridSpec& g = tgt.grid;
-        level = 0;
         active = (sx == sx && sy == sy && sz == sz) && ip.max_d2 > 0;
-        if (pass > 0) {
+        certified = !active;
+        if (pass > 0 && active) {
             const int pv = pr.prev[i];
             if (pv >= 0) {
                 double x, y, z;
@@ -454,23 +374,28 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                     // the previous match bounds the search ball; it stays unless something is strictly better
                     b.d2 = d2; b.idx = idx; b.pos = pv;
                     const double br = sqrt(d2) * (1.0 + 1e-9) + 1e-12;
-                    level = 0;
                     while (level < g.top_level && g.c0 * (double)(1 << level) < br) ++level;
+                    // Certificate from an earlier pass c: every other target point was at least lb2 away from this
+                    // source point's position then.  It moved by delta since, so every other point is still at least
+                    // lb2 - delta away: if the previous match is strictly closer, it is the unique nearest neighbour.
+                    const int c = pr.cert_pass[i];
+                    if (c != 255) {
+                        const double* Tc = st->Thist + 12 * c;
+                        const double ex = sx - (Tc[0] * px + Tc[1] * py + Tc[2] * pz + Tc[3]);
+                        const double ey = sy - (Tc[4] * px + Tc[5] * py + Tc[6] * pz + Tc[7]);
+                        const double ez = sz - (Tc[8] * px + Tc[9] * py + Tc[10] * pz + Tc[11]);
+                        const double delta = sqrt(ex * ex + ey * ey + ez * ez);
+                        if ((br + delta) * (1.0 + 1e-7) + 1e-9 < (double)pr.lb2[i]) { certified = true; cert_lb = -1.f; ++stat_skip; }
+                    }
                 }
             }
         }
     }
     // ---- union phase: the kG queries of a group are consecutive points of the Morton-sorted source, i.e. spatial
     // neighbours.  At the two finest levels their search balls share cells, so the group looks the union of the cells
-    // up once and every lane screens every staged record against its own query: no per-query set-up, no divergence
-    // (all lanes walk the same runs) and broadcast loads.  A lane is done when its best lies within the level's edge.
-    const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
-    const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
-    const long long tk1 = clock64();
-    bool certified = !active;
-    unsigned long long dbg_cand = 0;
-    int dbg_c0 = 0, dbg_c1 = 0, dbg_fb = 0, dbg_cells = 0;
-    long long tu_look = 0, tu_scan = 0, tu_bbox = 0;
+    // up once, stages the records in shared memory and every lane screens every staged record against its own
+    // query: no per-query set-up, no divergence, coalesced loads.  A lane is done when its best lies within the
+    // level's cell edge.  The two smallest screened distances give the lane its certificate for later passes.
     {
         const GridSpec g = tgt.grid;
         const TRec* __restrict__ trecs = reinterpret_cast<const TRec*>(tgt.recs);
@@ -481,10 +406,10 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
         const int gshift = lane & ~(kG - 1);
         for (int lu = 0; lu <= min(kUnionLevels - 1, g.top_level); ++lu) {
             const bool want = active && !certified && level <= lu;
-            if (!__any_sync(gmask, want)) continue;
-            const long long ta = clock64();
+            if (!__any_sync(gmask, want) || (ip.debug & 4)) continue;
             const double cl = g.c0 * (double)(1 << lu);
-            const double r = fmin((double)(sqrtf(__double2float_ru(b.d2)) * (1.0f + 1e-6f)) + 1e-12, cl);
+            // cells are selected for a ball slightly larger than needed: the margin is what later certificates live on
+            const double r = fmin((double)(sqrtf(__double2float_ru(b.d2)) * (1.0f + 1e-6f)) + 1e-12 + ip.cert_margin, cl);
             int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1, z0 = 1 << 30, z1 = -1;
             if (want) {
                 x0 = cell_coord(sx - r, g.ox, g.inv_c0) >> lu; x1 = cell_coord(sx + r, g.ox, g.inv_c0) >> lu;
@@ -498,28 +423,23 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 z0 = min(z0, __shfl_xor_sync(gmask, z0, o, kG)); z1 = max(z1, __shfl_xor_sync(gmask, z1, o, kG));
             }
             const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
-            const long long tb = clock64();
-            tu_bbox += tb - ta;
             if (ncell > kUnionMax) break;            // the group straddles a jump of the space-filling curve: serve lanes one by one
             int nr = 0;
             for (int base = 0; base < ncell; base += kG) {
                 const int t = base + gl;
                 bool valid = false;
-                unsigned st = 0, en = 0;
+                unsigned rs = 0, re = 0;
                 if (t < ncell) {
                     const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
-                    valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(cx, cy, cz), st, en);
+                    valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(cx, cy, cz), rs, re);
                 }
                 const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
-                if (valid) runs[nr + __popc(vm & ((1u << gl) - 1u))] = make_uint2(st, en);
+                if (valid) runs[nr + __popc(vm & ((1u << gl) - 1u))] = make_uint2(rs, re);
                 nr += __popc(vm);
             }
             __syncwarp(gmask);
-            const long long tc = clock64();
-            tu_look += tc - tb;
+            float f1 = INFINITY, f2 = INFINITY;     // two smallest screened float32 distances (multiset)
             if constexpr (!TW) {
-                // stage the union's records in shared memory, kStage at a time: every lane fetches different records
-                // (coalesced, many loads in flight), then all lanes screen the staged records against their own query
                 float4* stage = s_stage[grp];
                 int* spos = s_spos[grp];
                 int rr = 0;
@@ -537,13 +457,14 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                         off += len;
                         if (run.x + off >= run.y) { ++rr; off = 0; }
                     }
-                    if (lu == 0) dbg_cand += (gl == 0) ? fill : 0; else dbg_cells += (gl == 0) ? fill : 0;
                     __syncwarp(gmask);
 #pragma unroll 8
                     for (int j = 0; j < fill; ++j) {
                         const float4 v = stage[j];
                         const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
                         const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        f2 = fminf(f2, fmaxf(f1, d2f));
+                        f1 = fminf(f1, d2f);
                         if (want && d2f <= thr) {
                             const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
                             const int idx = __float_as_int(v.w);
@@ -565,81 +486,66 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 }
             }
             __syncwarp(gmask);
-            tu_scan += clock64() - tc;
             if (want) {
                 // every target point within min(previous bound, cl) of this lane's query was screened
-                if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) { certified = true; if (lu == 0) ++dbg_c0; else ++dbg_c1; }
-                else level = lu + 1;
-            }
-        }
-    }
-    const long long tk2 = clock64();
-    // ---- remaining queries (nearest neighbour beyond the union levels): kG lanes serve them one after the other
-    {
-        for (int k = 0; k < kG; ++k) {
-            const bool qa = __shfl_sync(gmask, (int)(active && !certified), k, kG) != 0;
-            if (!qa) continue;
-            if (gl == k) ++dbg_fb;
-            const double qx = __shfl_sync(gmask, sx, k, kG), qy = __shfl_sync(gmask, sy, k, kG), qz = __shfl_sync(gmask, sz, k, kG);
-            const double qd2 = __shfl_sync(gmask, b.d2, k, kG);
-            const int qidx = __shfl_sync(gmask, b.idx, k, kG), ql = __shfl_sync(gmask, level, k, kG);
-            Best lb;
-            const bool hv = group_search<TW>(tgt, qx, qy, qz, qd2, qidx, ql, ip.defer_level, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
-            if (gl == k) {
-                if (lb.pos >= 0) b = lb;
-                heavy = hv;
-            }
-        }
-    }
-    const long long tk3 = clock64();
-    if (ip.debug) {
-        const unsigned long long c0 = warp_sum(dbg_c0), c1 = warp_sum(dbg_c1), fb = warp_sum(dbg_fb), hv = warp_sum(heavy ? 1 : 0),
-                                 ce = warp_sum(dbg_cells), ac = warp_sum(active ? 1 : 0);
-        unsigned long long cand = dbg_cand;
-        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(kFull, cand, o);
-        if (lane == 0) {
-            atomicAdd(&st->dbg[0], cand); atomicAdd(&st->dbg[1], c0); atomicAdd(&st->dbg[2], c1); atomicAdd(&st->dbg[3], fb);
-            atomicAdd(&st->dbg[4], hv); atomicAdd(&st->dbg[5], ce); atomicAdd(&st->dbg[6], ac);
-        }
-    }
-    // ---- deferred (far) queries: the whole block serves them one at a time
-    {
-        __shared__ int s_nheavy, s_nruns;
-        __shared__ unsigned char s_hlist[kIcpBlock];
-        __shared__ uint2 s_runs[kMaxRuns];
-        __shared__ double s_q[4];
-        __shared__ int s_qi;
-        __shared__ double s_wd2[kIcpBlock / 32];
-        __shared__ int s_widx[kIcpBlock / 32], s_wpos[kIcpBlock / 32];
-        if (threadIdx.x == 0) s_nheavy = 0;
-        __syncthreads();
-        if (heavy) s_hlist[atomicAdd(&s_nheavy, 1)] = (unsigned char)threadIdx.x;
-        __syncthreads();
-        const int nheavy = s_nheavy;
-        for (int h = 0; h < nheavy; ++h) {
-            const int owner = s_hlist[h];
-            if ((int)threadIdx.x == owner) { s_q[0] = sx; s_q[1] = sy; s_q[2] = sz; s_q[3] = b.d2; s_qi = b.idx; }
-            __syncthreads();
-            Best lb;
-            block_search<TW>(tgt, s_q[0], s_q[1], s_q[2], s_q[3], s_qi, lb, s_runs, &s_nruns);
-            const int w = threadIdx.x >> 5;
-            if (lane == 0) { s_wd2[w] = lb.d2; s_widx[w] = lb.idx; s_wpos[w] = lb.pos; }
-            __syncthreads();
-            if ((int)threadIdx.x == owner) {
-                Best r = b;
-                int rpos = -1;
-                for (int ww = 0; ww < kIcpBlock / 32; ++ww)
-                    if (s_wpos[ww] >= 0 && (s_wd2[ww] < r.d2 || (s_wd2[ww] == r.d2 && s_widx[ww] < r.idx))) {
-                        r.d2 = s_wd2[ww]; r.idx = s_widx[ww]; rpos = s_wpos[ww];
+                if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) {
+                    certified = true;
+                    ++stat_union;
+                    if (!TW && b.pos >= 0) {
+                        // lower bound on the distance to every target point but the match: screened points via the second
+                        // smallest float32 distance (minus its error bound), all others lie outside the selected cells
+                        const float low2 = f2 * (1.0f - 4e-6f) - 3.6f * e * sqrtf(f2) - 3.1f * e * e;
+                        const float l2 = low2 > 0.f ? sqrtf(low2) * (1.0f - 1e-6f) : 0.f;
+                        cert_lb = fminf(l2, (float)r * (1.0f - 1e-6f));
                     }
-                if (rpos >= 0) { r.pos = rpos; b = r; }
+                } else {
+                    level = lu + 1;
+                }
             }
-            __syncthreads();
         }
     }
-    const long long tk4 = clock64();
+    // ---- remaining queries (nearest neighbour beyond the union levels): the warp's pending queries are dealt round
+    // robin to its 32/kG groups, each group serving one query at a time with the cooperative branch-and-bound search
+    {
+        const unsigned pend = __ballot_sync(kFull, active && !certified && !(ip.debug & 2));
+        const int npend = __popc(pend);
+        constexpr int kGroupsPerWarp = 32 / kG;
+        const int wg = lane / kG;                      // group index inside the warp
+        for (int base = 0; base < npend; base += kGroupsPerWarp) {
+            const int item = base + wg;                // the item-th pending lane of the warp (ascending lane order)
+            int owner = -1;
+            if (item < npend) owner = __fns(pend, 0, item + 1);
+            const int src_lane = owner >= 0 ? owner : 0;
+            const double qx = __shfl_sync(kFull, sx, src_lane), qy = __shfl_sync(kFull, sy, src_lane), qz = __shfl_sync(kFull, sz, src_lane);
+            const double qd2 = __shfl_sync(kFull, b.d2, src_lane);
+            const int qidx = __shfl_sync(kFull, b.idx, src_lane), ql = __shfl_sync(kFull, level, src_lane);
+            Best lb;
+            lb.d2 = 0; lb.idx = 0; lb.pos = -1;
+            if (owner >= 0) group_search<TW>(tgt, qx, qy, qz, qd2, qidx, ql, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
+            // hand the results back: the lane that owns item j reads them from group j % kGroupsPerWarp
+            const int my_item = (active && !certified) ? __popc(pend & ((1u << lane) - 1u)) : -1;
+            const bool mine = my_item >= base && my_item < base + kGroupsPerWarp;
+            const int from = mine ? (my_item - base) * kG : 0;
+            const double rd2 = __shfl_sync(kFull, lb.d2, from);
+            const int ridx = __shfl_sync(kFull, lb.idx, from), rpos = __shfl_sync(kFull, lb.pos, from);
+            if (mine) {
+                if (rpos >= 0) { b.d2 = rd2; b.idx = ridx; b.pos = rpos; }
+                ++stat_fb;
+            }
+        }
+    }
+
+    // ---- per lane: residual / Jacobian (point-to-plane) or Umeyama moments (point-to-point)
+    double acc[kNS];
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
     if (i < n) {
         pr.prev[i] = b.pos;
+        if (cert_lb >= 0.f) {      // < 0: an older certificate was used and stays valid
+            const bool ok = cert_lb > 0.f && pass < kThist;
+            pr.cert_pass[i] = ok ? (unsigned char)pass : (unsigned char)255;
+            if (ok) pr.lb2[i] = cert_lb;
+        }
         if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = b.pos >= 0 ? b.idx : -1;
         if (b.pos >= 0) {
             double tx, ty, tz;
@@ -666,45 +572,43 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             }
         }
     }
-    // warp -> block reduction in a fixed order (bit-reproducible run to run)
-    const int w = threadIdx.x >> 5;
+    // warp reduction in a fixed order; one row of partial sums per warp (bit-reproducible run to run)
+    double* row = pr.partials + ((size_t)blockIdx.x * (kIcpBlock / 32) + (threadIdx.x >> 5)) * kSumStride;
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         if (METHOD == 0 && k >= 15 && k < 27) continue;
         const double v = warp_sum(acc[k]);
-        if (lane == 0) s_red[w][k] = v;
+        if (lane == 0) row[k] = v;
     }
-    __syncthreads();
-    if (threadIdx.x < kNS) {
-        double v = 0;
-        if (!(METHOD == 0 && threadIdx.x >= 15 && threadIdx.x < 27)) {
-#pragma unroll
-            for (int ww = 0; ww < kIcpBlock / 32; ++ww) v += s_red[ww][threadIdx.x];
-        }
-        pr.partials[(size_t)blockIdx.x * kSumStride + threadIdx.x] = v;
+    if (ip.debug & 1) {
+        const int a = warp_sum(stat_skip), u = warp_sum(stat_union), f = warp_sum(stat_fb);
+        if (lane == 0) { row[29] = (double)a; row[30] = (double)u; row[31] = (double)f; }
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const long long tk5 = clock64();
-        if (ip.debug) {
-        atomicAdd(&st->tl[0], (unsigned long long)(tk1 - tk0)); atomicAdd(&st->tl[1], (unsigned long long)(tk2 - tk1));
-        atomicAdd(&st->tl[2], (unsigned long long)(tk3 - tk2)); atomicAdd(&st->tl[3], (unsigned long long)(tk4 - tk3));
-        atomicAdd(&st->tl[4], (unsigned long long)(tk5 - tk4)); atomicAdd(&st->tl[5], 1ull);
-        atomicAdd(&st->dbg[7], (unsigned long long)tu_scan); atomicAdd(&st->tl[7], (unsigned long long)tu_look);
-        }
-        const unsigned t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == (unsigned)nblk - 1u) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
+}
 
-    // ---- last block of this pair: grid reduction, solve, convergence test -------------------------------
+// Finish kernel, one block per pair: fixed-order reduction of the warps' partial sums, solve, cumulative
+// transformation update and Open3D's convergence test.  Sets the `done` flag that turns later passes into no-ops.
+template <int METHOD>
+__global__ void __launch_bounds__(256) k_icp_finish(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+    __shared__ double s_part[8][kSumStride];
     __shared__ double s_sum[kSumStride];
-    if (threadIdx.x < kNS) {
-        double v = 0;
-        for (int bb = 0; bb < nblk; ++bb) v += __ldcg(pr.partials + (size_t)bb * kSumStride + threadIdx.x);
-        s_sum[threadIdx.x] = v;
+    const PairDev& pr = pairs[blockIdx.x];
+    PairState* st = pr.state;
+    if (st->done) return;
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    const int n = src.counts[CNT_NPTS];
+    const int nrows = max(1, (n + kIcpBlock - 1) / kIcpBlock) * (kIcpBlock / 32);
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    double v = 0;
+    for (int r = w; r < nrows; r += 8) v += pr.partials[(size_t)r * kSumStride + lane];
+    s_part[w][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < kSumStride) {
+        double t = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) t += s_part[ww][threadIdx.x];
+        s_sum[threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -713,7 +617,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
         const double rmse = K > 0 ? sqrt(s_sum[27] / K) : 0.0;
         if (pr.state_trace) {
             double* tr = pr.state_trace + (size_t)pass * 18;
-            for (int k = 0; k < 16; ++k) tr[k] = s_T[k];
+            for (int k = 0; k < 16; ++k) tr[k] = st->T[k];
             tr[16] = fitness; tr[17] = rmse;
         }
         bool stop = pass >= ip.max_iter;
@@ -723,19 +627,18 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
         st->ncorr = (int)K;
         st->passes = pass + 1;
         for (int k = 0; k < kNS; ++k) st->sums[k] = s_sum[k];
+        if (ip.debug & 1) { st->dbg[0] += (unsigned long long)s_sum[29]; st->dbg[1] += (unsigned long long)s_sum[30]; st->dbg[2] += (unsigned long long)s_sum[31]; st->dbg[3] += (unsigned long long)n; }
         if (stop) {
             st->done = 1;
         } else {
             double upd[16], Tn[16];
             solve_update(METHOD, s_sum, upd);
-            mat4_mul(upd, s_T, Tn);
+            mat4_mul(upd, st->T, Tn);
             for (int k = 0; k < 16; ++k) st->T[k] = Tn[k];
+            if (pass + 1 < kThist) for (int k = 0; k < 12; ++k) st->Thist[12 * (pass + 1) + k] = Tn[k];
             st->updates = st->updates + 1;
         }
         st->err = src.counts[CNT_ERR] | tgt.counts[CNT_ERR];
-        if (ip.debug) atomicAdd(&st->tl[6], (unsigned long long)(clock64() - tk0));
-        st->ticket = 0u;
-        __threadfence();
     }
 }
 
@@ -756,6 +659,7 @@ static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, const 
     if (combos_mask & 2) L.launch(nm, k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
     if (combos_mask & 4) L.launch(nm, k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
     if (combos_mask & 8) L.launch(nm, k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    L.launch("icp_finish", k_icp_finish<METHOD>, dim3(grid.y), dim3(256), d_pairs, ip, pass);
 }
 
 // combos_mask bit (2*src_wide + tgt_wide) set when some pair of the batch has that record-type combination
