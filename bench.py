@@ -117,6 +117,7 @@ def cpu_pairs_per_sec(seq, n_pairs):
     """The oracle (C++/OpenMP float64 restatement of the reference's Open3D CPU path) on all host threads:
     preprocessing of every scan once + ICP of consecutive pairs, like run_scanmatcher.py:191-213."""
     from oracle import oracle as orc
+    orc.set_num_threads(os.cpu_count() or 1)    # torchrun exports OMP_NUM_THREADS=1: use every host thread anyway
     pre = [orc.preprocess(seq.scans[0])]        # steady state of consecutive matching: one new scan per pair
     t0 = time.perf_counter()
     for k in range(n_pairs):

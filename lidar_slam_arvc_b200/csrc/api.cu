@@ -326,7 +326,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     NormalParams np{};
     np.radius = p->normal_radius; np.max_nn = p->max_nn; np.level = 0;
     if (want_normals)
-        while (np.level < kMortonBits && c0 * (double)(1 << np.level) < p->normal_radius * (1.0 + 1e-6)) ++np.level;
+        while (np.level < kMortonBits && c0 * (double)(1 << np.level) < p->normal_radius * (1.0 - 1e-12)) ++np.level;
 
     VoxelParams vp{};
     if (voxel_on) {
@@ -614,11 +614,11 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     int err = 0;
     if (getenv("ARVC_DEBUG_STATS")) {
-        unsigned long long tot[4] = {0};
+        unsigned long long tot[8] = {0};
         long long passes = 0;
-        for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 4; ++k) tot[k] += pb.h_states[i].dbg[k]; passes += pb.h_states[i].passes; }
-        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu skipped_by_certificate=%llu union=%llu fallback=%llu\n", pb.n_pairs, passes,
-                tot[3], tot[0], tot[1], tot[2]);
+        for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 8; ++k) tot[k] += pb.h_states[i].dbg[k]; passes += pb.h_states[i].passes; }
+        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu skipped_by_certificate=%llu union=%llu fallback=%llu (start level 2:%llu 3:%llu 4:%llu 5+:%llu)\n", pb.n_pairs, passes,
+                tot[3], tot[0], tot[1], tot[2], tot[4], tot[5], tot[6], tot[7]);
     }
     for (int i = 0; i < pb.n_pairs; ++i) {
         const PairState& st = pb.h_states[i];

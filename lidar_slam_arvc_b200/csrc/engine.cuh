@@ -11,7 +11,14 @@ namespace arvc {
 
 struct FilterParams { double min_r2, max_r2, min_h, max_h; };
 struct VoxelParams { double voxel; int bx, by, bz, pad; };
-struct NormalParams { double radius; int max_nn; int level; };
+struct NormalParams {
+    double radius, r2, bin_scale;       // r2 = radius^2, bin_scale = buckets / r2
+    float r2_lo, r2_hi, bin_scale_f;    // float32 screening bounds r2 * (1 -/+ 2e-6)
+    int max_nn;
+    int level;
+    int debug;
+    int pad;
+};
 
 struct Launcher {
     cudaStream_t stream = nullptr;
@@ -59,11 +66,11 @@ struct __align__(16) PairState {
     int ncorr;
     int err;                // OR of the two scans' device error flags
     int pad[3];
-    unsigned long long dbg[4];   // search statistics (ARVC_DEBUG_STATS): skipped / union / fallback queries, queries
+    unsigned long long dbg[8];   // search statistics (ARVC_DEBUG_STATS): skipped / union / fallback queries, queries, fallback by level
     // ---- device-only tail (not copied back): top three rows of the transformation each pass was evaluated at
     double Thist[12 * kThist];
 };
-constexpr size_t kPairStateHead = 16 * 8 + 2 * 8 + 32 * 8 + 8 * 4 + 4 * 8;   // bytes read back per pair
+constexpr size_t kPairStateHead = 16 * 8 + 2 * 8 + 32 * 8 + 8 * 4 + 8 * 8;   // bytes read back per pair
 
 struct PairDev {
     const ScanDev* src;

@@ -33,7 +33,8 @@ constexpr int kG = 8;            // lanes per query
 constexpr int kBigRun = 160;     // longer runs are expanded into their children instead of scanned
 constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
-constexpr int kUnionLevels = 2;  // finest levels served by the shared-candidate (union) phase
+constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
+constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may hold
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
 
@@ -423,8 +424,9 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 z0 = min(z0, __shfl_xor_sync(gmask, z0, o, kG)); z1 = max(z1, __shfl_xor_sync(gmask, z1, o, kG));
             }
             const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
-            if (ncell > kUnionMax) break;            // the group straddles a jump of the space-filling curve: serve lanes one by one
-            int nr = 0;
+            // sparse regions / jumps of the space-filling curve: the 8 queries span too many cells here, try a coarser level
+            if (ncell > kUnionMax) continue;
+            int nr = 0, utotal = 0;
             for (int base = 0; base < ncell; base += kG) {
                 const int t = base + gl;
                 bool valid = false;
@@ -436,8 +438,13 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                 const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
                 if (valid) runs[nr + __popc(vm & ((1u << gl) - 1u))] = make_uint2(rs, re);
                 nr += __popc(vm);
+                utotal += (int)(re - rs);
             }
+#pragma unroll
+            for (int o = kG / 2; o > 0; o >>= 1) utotal += __shfl_xor_sync(gmask, utotal, o, kG);
             __syncwarp(gmask);
+            // coarse levels pay off only where the scan is sparse; dense unions are left to the per-query search
+            if (lu >= 2 && utotal > kUnionCandCap) { if ((ip.debug & 1) && want) atomicAdd(&pr.state->dbg[7], 1ull); break; }
             float f1 = INFINITY, f2 = INFINITY;     // two smallest screened float32 distances (multiset)
             if constexpr (!TW) {
                 float4* stage = s_stage[grp];
@@ -531,6 +538,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             if (mine) {
                 if (rpos >= 0) { b.d2 = rd2; b.idx = ridx; b.pos = rpos; }
                 ++stat_fb;
+                if (ip.debug & 1) atomicAdd(&pr.state->dbg[4 + min(max(level - 2, 0), 3)], 1ull);
             }
         }
     }

@@ -6,6 +6,9 @@
 // -> Open3D EstimatePerPointCovariances (SearchHybrid, ComputeCovariance) + ComputeNormal (FastEigen3x3).
 // Selection of the k nearest among more than k in-radius neighbours is exact: a monotone d2-histogram
 // finds the bucket holding the k-th neighbour, the bucket is ranked exactly by (d2, index).
+#include <cstdio>
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace arvc {
@@ -114,8 +117,11 @@ constexpr int kCanon = 320;          // most neighbours the canonical (sorted, s
 // per-warp shared memory, two layouts that are never live at the same time:
 //   selection : int hist[kBins] | double cand_d2[kCand] | int cand_idx[kCand] | int cand_pos[kCand]
 //   canonical : double key_d2[kCanon] | int key_idx[kCanon] | int key_pos[kCanon] | int order[kCanon]
-constexpr int kWarpSmem = kCanon * 20;
-static_assert(kBins * 4 + kCand * 16 <= kWarpSmem, "selection layout must fit");
+constexpr int kScratch = kCanon * 20;  // bytes of the two overlapping layouts above
+constexpr int kTryRuns = 160;          // cells of the trial ball (6^3 = 216 before box pruning)
+constexpr int kWarpSmem = kScratch + (64 + kTryRuns) * 8;   // + cell runs, which outlive both layouts
+constexpr int kDenseFactor = 3;        // neighbourhoods with more than kDenseFactor * max_nn candidates try a smaller radius first
+static_assert(kBins * 4 + kCand * 16 <= kScratch, "selection layout must fit");
 constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
 
 __device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
@@ -177,106 +183,89 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
 
     const GridSpec g = s.grid;
     const int L = np.level;
-    const double r2 = np.radius * np.radius;
-    const float r2_lo = (float)(r2 * (1.0 - 2e-6)), r2_hi = (float)(r2 * (1.0 + 2e-6));
+    const double r2 = np.r2;
+    const float r2_lo = np.r2_lo, r2_hi = np.r2_hi;
     const double rinf = np.radius * (1.0 + 1e-9) + 1e-12;
     const double cl = g.c0 * (double)(1 << L);
     const int x0 = cell_coord(qx - rinf, g.ox, g.inv_c0) >> L, x1 = cell_coord(qx + rinf, g.ox, g.inv_c0) >> L;
     const int y0 = cell_coord(qy - rinf, g.oy, g.inv_c0) >> L, y1 = cell_coord(qy + rinf, g.oy, g.inv_c0) >> L;
     const int z0 = cell_coord(qz - rinf, g.oz, g.inv_c0) >> L, z1 = cell_coord(qz + rinf, g.oz, g.inv_c0) >> L;
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-    const int ncell = nx * ny * nz;            // <= 27: the host picks the level with cell edge >= radius
+    const int ncell = nx * ny * nz;            // <= 27 (64 when the inflated ball grazes a fourth cell): cell edge >= radius
 
     unsigned char* wmem = s_raw + (size_t)w * kWarpSmem;
     int* hist = reinterpret_cast<int*>(wmem);
     double* cand_d2 = reinterpret_cast<double*>(wmem + kBins * 4);
     int* cand_idx = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 8);
     int* cand_pos = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 12);
+    uint2* runs_full = reinterpret_cast<uint2*>(wmem + kScratch);           // <= 64 runs: cells of the full radius
+    uint2* runs_try = runs_full + 64;                                       // <= kTryRuns runs: finer cells of the trial radius
 
-    // look the (<= 27) cells up once: lane c owns cell c; cells whose box misses the ball are skipped
-    unsigned st = 0, en = 0;
-    if (lane < ncell) {
-        const int cx = x0 + lane % nx, cy = y0 + (lane / nx) % ny, cz = z0 + lane / (nx * ny);
-        const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
-        const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cl)));
-        const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cl)));
-        const double ddz = fmax(0.0, fmax(bz0 - qz, qz - (bz0 + cl)));
-        if (ddx * ddx + ddy * ddy + ddz * ddz <= r2 * (1.0 + 1e-9) + 1e-12)
-            grid_lookup(s.table, s.table_mask, L, morton3(cx, cy, cz), st, en);
+    // ---- cells of the full radius (<= 27 at the level whose edge >= radius): lane c owns cell c
+    int nfull = 0, total = 0;
+    for (int base = 0; base < ncell; base += 32) {      // one round unless the ball grazes a fourth cell along an axis
+        const int t = base + lane;
+        unsigned st = 0, en = 0;
+        bool valid = false;
+        if (t < ncell) {
+            const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
+            const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
+            const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cl)));
+            const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cl)));
+            const double ddz = fmax(0.0, fmax(bz0 - qz, qz - (bz0 + cl)));
+            if (ddx * ddx + ddy * ddy + ddz * ddz <= r2 * (1.0 + 1e-9) + 1e-12)
+                valid = grid_lookup(s.table, s.table_mask, L, morton3(cx, cy, cz), st, en);
+        }
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (valid) runs_full[nfull + __popc(vm & ((1u << lane) - 1u))] = make_uint2(st, en);
+        nfull += __popc(vm);
+        total += warp_sum((int)(en - st));
     }
-    const int total = warp_sum((int)(en - st));
-
-    // d2 -> bucket, monotone in the exact d2; the float32 shortcut is taken only when it cannot cross a bucket edge
-    const double bin_scale = (double)kBins / r2;
-    const float bin_scale_f = (float)bin_scale;
-    auto bucket = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> int {
-        if constexpr (!WIDE) {
-            const float u = c.d2f * bin_scale_f;
-            const int b = (int)u;
-            const float fr = u - (float)b;
-            if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) return b;
-        }
-        if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
-        return min(kBins - 1, (int)(d2 * bin_scale));
-    };
-    // membership in the radius, exact
-    auto in_radius = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> bool {
-        const int t = c.below(r2_lo, r2_hi);
-        if (t != 0) return t > 0;
-        if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
-        return d2 < r2;
-    };
-
-    int bstar = kBins, need = 0;       // buckets < bstar are taken whole; `need` more come from bucket bstar
-    if (total > np.max_nn) {
-        // ---- pass A: bucket histogram of the in-radius candidates
-        for (int b = lane; b < kBins; b += 32) hist[b] = 0;
-        __syncwarp();
-        for (int cc = 0; cc < ncell; ++cc) {
-            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-            for (unsigned j = cst + lane; j < cen; j += 32) {
-                CandEval<WIDE> c;
-                c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                double d2 = 0;
-                bool have = false;
-                if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
-            }
-        }
-        __syncwarp();
-        constexpr int per = kBins / 32;      // lane owns `per` consecutive buckets
-        int local = 0;
-#pragma unroll
-        for (int b = 0; b < per; ++b) local += hist[lane * per + b];
-        int inc = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
-        }
-        const int n_in = __shfl_sync(kFull, inc, 31);
-        if (n_in > np.max_nn) {
-            int before = inc - local, myb = -1, myneed = 0;
-            if (before < np.max_nn && inc >= np.max_nn) {
-#pragma unroll
-                for (int b = 0; b < per; ++b) {
-                    const int h = hist[lane * per + b];
-                    if (myb < 0 && before + h >= np.max_nn) { myb = lane * per + b; myneed = np.max_nn - before; }
-                    before += h;
+    // ---- dense neighbourhoods: the k nearest lie well inside the radius.  Estimate their radius from the local
+    // density (k / total of the 3x3x3 block, surface model), cover that smaller ball with cells one level finer and
+    // let the histogram pass verify the guess: if it holds fewer than k points, fall back to the full radius.
+    int ntry = 0, total_try = 0;
+    double rtry = 0.0;
+    if (total > kDenseFactor * np.max_nn && L > 0) {
+        rtry = 1.35 * 3.0 * cl * sqrt((double)np.max_nn / (3.141592653589793 * (double)total));
+        if (rtry < 0.8 * np.radius) {
+            const int Lf = L - 1;
+            const double cf = 0.5 * cl, rt = rtry * (1.0 + 1e-9) + 1e-12, rt2 = rtry * rtry;
+            const int fx0 = cell_coord(qx - rt, g.ox, g.inv_c0) >> Lf, fx1 = cell_coord(qx + rt, g.ox, g.inv_c0) >> Lf;
+            const int fy0 = cell_coord(qy - rt, g.oy, g.inv_c0) >> Lf, fy1 = cell_coord(qy + rt, g.oy, g.inv_c0) >> Lf;
+            const int fz0 = cell_coord(qz - rt, g.oz, g.inv_c0) >> Lf, fz1 = cell_coord(qz + rt, g.oz, g.inv_c0) >> Lf;
+            const int fnx = fx1 - fx0 + 1, fny = fy1 - fy0 + 1, fncell = fnx * fny * (fz1 - fz0 + 1);
+            for (int base = 0; base < fncell; base += 32) {
+                const int t = base + lane;
+                unsigned st = 0, en = 0;
+                bool valid = false;
+                if (t < fncell) {
+                    const int cx = fx0 + t % fnx, cy = fy0 + (t / fnx) % fny, cz = fz0 + t / (fnx * fny);
+                    const double bx0 = g.ox + cx * cf, by0 = g.oy + cy * cf, bz0 = g.oz + cz * cf;
+                    const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cf)));
+                    const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cf)));
+                    const double ddz = fmax(0.0, fmax(bz0 - qz, qz - (bz0 + cf)));
+                    if (ddx * ddx + ddy * ddy + ddz * ddz <= rt2 * (1.0 + 1e-9) + 1e-12)
+                        valid = grid_lookup(s.table, s.table_mask, Lf, morton3(cx, cy, cz), st, en);
                 }
+                const unsigned vm = __ballot_sync(kFull, valid);
+                const int slot = ntry + __popc(vm & ((1u << lane) - 1u));
+                if (valid && slot < kTryRuns) runs_try[slot] = make_uint2(st, en);
+                ntry += __popc(vm);
+                total_try += warp_sum((int)(en - st));
             }
-            const unsigned who = __ballot_sync(kFull, myb >= 0);
-            const int src_lane = __ffs(who) - 1;
-            bstar = __shfl_sync(kFull, myb, src_lane);
-            need = __shfl_sync(kFull, myneed, src_lane);
+            if (ntry > kTryRuns || total_try <= np.max_nn) ntry = 0;      // does not fit / cannot hold k points: full radius
         }
-        __syncwarp();
     }
+    __syncwarp();
 
-    // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    int cnt = 0, ncand = 0;
-    double tau_d2 = r2;      // selected <=> d2 < r2 and (d2, idx) <= (tau_d2, tau_idx)
+    int cnt = 0;
+    double tau_d2 = r2;      // selected <=> d2 < rq2 and (d2, idx) <= (tau_d2, tau_idx)
     int tau_idx = 0x7fffffff;
+    double rq2 = r2;         // radius^2 the neighbourhood was finally searched with
+    const uint2* runs = runs_full;
+    int nruns = nfull;
     auto accumulate = [&](double x, double y, double z) {
         const double ux = x - qx, uy = y - qy, uz = z - qz;      // centred: exact differences of float32 payloads
         sx += ux; sy += uy; sz += uz;
@@ -284,99 +273,181 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         syy = fma(uy, uy, syy); syz = fma(uy, uz, syz); szz = fma(uz, uz, szz);
         ++cnt;
     };
-    for (int cc = 0; cc < ncell; ++cc) {
-        const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-        for (unsigned t = cst; t < cen; t += 32) {
-            const unsigned j = t + lane;
-            bool hit = false;
-            double d2 = 0;
-            CandEval<WIDE> c;
-            if (j < cen) {
-                c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                bool have = false;
-                if (in_radius(c, d2, have)) {
-                    const int b = bstar == kBins ? 0 : bucket(c, d2, have);
-                    if (b < bstar) accumulate(c.x(), c.y(), c.z());
-                    else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
+
+    for (int attempt = (ntry > 0 ? 0 : 1); attempt < 2; ++attempt) {
+        const bool trial = attempt == 0;
+        runs = trial ? runs_try : runs_full;
+        nruns = trial ? ntry : nfull;
+        rq2 = trial ? rtry * rtry : r2;
+        const int tot = trial ? total_try : total;
+        const double bin_scale = trial ? (double)kBins / rq2 : np.bin_scale;
+        const float bin_scale_f = (float)bin_scale;
+        const float rq2_lo = trial ? (float)(rq2 * (1.0 - 2e-6)) : np.r2_lo, rq2_hi = trial ? (float)(rq2 * (1.0 + 2e-6)) : np.r2_hi;
+        // d2 -> bucket, monotone in the exact d2; the float32 shortcut is taken only when it cannot cross a bucket edge
+        auto bucket = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> int {
+            if constexpr (!WIDE) {
+                const float u = c.d2f * bin_scale_f;
+                const int b = (int)u;
+                const float fr = u - (float)b;
+                if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) return b;
+            }
+            if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
+            return min(kBins - 1, (int)(d2 * bin_scale));
+        };
+        auto in_radius = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> bool {      // exact membership
+            const int t = c.below(rq2_lo, rq2_hi);
+            if (t != 0) return t > 0;
+            if (!have) { d2 = c.exact(qx, qy, qz); have = true; }
+            return d2 < rq2;
+        };
+
+        int bstar = kBins, need = 0;       // buckets < bstar are taken whole; `need` more come from bucket bstar
+        if (tot > np.max_nn) {
+            // ---- pass A: bucket histogram of the in-radius candidates
+            for (int b = lane; b < kBins; b += 32) hist[b] = 0;
+            __syncwarp();
+            for (int rr = 0; rr < nruns; ++rr) {
+                const uint2 run = runs[rr];
+                for (unsigned j = run.x + lane; j < run.y; j += 32) {
+                    CandEval<WIDE> c;
+                    c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                    double d2 = 0;
+                    bool have = false;
+                    if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
                 }
             }
-            if (bstar != kBins) {
-                const unsigned m = __ballot_sync(kFull, hit);
-                if (hit) {
-                    const int slot = ncand + __popc(m & ((1u << lane) - 1u));
-                    if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+            __syncwarp();
+            constexpr int per = kBins / 32;      // lane owns `per` consecutive buckets
+            int local = 0;
+#pragma unroll
+            for (int b = 0; b < per; ++b) local += hist[lane * per + b];
+            int inc = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int n_in = __shfl_sync(kFull, inc, 31);
+            if (trial && n_in < np.max_nn) continue;          // the guess was too small: search the full radius
+            if (n_in > np.max_nn) {
+                int before = inc - local, myb = -1, myneed = 0;
+                if (before < np.max_nn && inc >= np.max_nn) {
+#pragma unroll
+                    for (int b = 0; b < per; ++b) {
+                        const int h = hist[lane * per + b];
+                        if (myb < 0 && before + h >= np.max_nn) { myb = lane * per + b; myneed = np.max_nn - before; }
+                        before += h;
+                    }
                 }
-                ncand += __popc(m);
+                const unsigned who = __ballot_sync(kFull, myb >= 0);
+                const int src_lane = __ffs(who) - 1;
+                bstar = __shfl_sync(kFull, myb, src_lane);
+                need = __shfl_sync(kFull, myneed, src_lane);
+            }
+            __syncwarp();
+        }
+
+        // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
+        int ncand = 0;
+        for (int rr = 0; rr < nruns; ++rr) {
+            const uint2 run = runs[rr];
+            for (unsigned t = run.x; t < run.y; t += 32) {
+                const unsigned j = t + lane;
+                bool hit = false;
+                double d2 = 0;
+                CandEval<WIDE> c;
+                if (j < run.y) {
+                    c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                    bool have = false;
+                    if (in_radius(c, d2, have)) {
+                        const int b = bstar == kBins ? 0 : bucket(c, d2, have);
+                        if (b < bstar) accumulate(c.x(), c.y(), c.z());
+                        else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
+                    }
+                }
+                if (bstar != kBins) {
+                    const unsigned m = __ballot_sync(kFull, hit);
+                    if (hit) {
+                        const int slot = ncand + __popc(m & ((1u << lane) - 1u));
+                        if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                    }
+                    ncand += __popc(m);
+                }
             }
         }
-    }
-    if (bstar != kBins) {
-        __syncwarp();
-        if (ncand <= kCand) {
-            // exact rank inside the boundary bucket; the `need` smallest (d2, index) keys join the neighbourhood
-            double td2 = 0;
-            int tidx = 0;
-            bool have_tau = false;
-            for (int a = lane; a < ncand; a += 32) {
-                const double d2a = cand_d2[a];
-                const int ia = cand_idx[a];
-                int rank = 0;
-                for (int b = 0; b < ncand; ++b) rank += key_less(cand_d2[b], cand_idx[b], d2a, ia) ? 1 : 0;
-                if (rank < need) {
-                    double x, y, z;
-                    int idx;
-                    load_rec(recs + cand_pos[a], x, y, z, idx);
-                    accumulate(x, y, z);
+        if (bstar != kBins) {
+            __syncwarp();
+            if (ncand <= kCand) {
+                // exact rank inside the boundary bucket; the `need` smallest (d2, index) keys join the neighbourhood
+                double td2 = 0;
+                int tidx = 0;
+                bool have_tau = false;
+                for (int a = lane; a < ncand; a += 32) {
+                    const double d2a = cand_d2[a];
+                    const int ia = cand_idx[a];
+                    int rank = 0;
+                    for (int b = 0; b < ncand; ++b) rank += key_less(cand_d2[b], cand_idx[b], d2a, ia) ? 1 : 0;
+                    if (rank < need) {
+                        double x, y, z;
+                        int idx;
+                        load_rec(recs + cand_pos[a], x, y, z, idx);
+                        accumulate(x, y, z);
+                    }
+                    if (rank == need - 1) { td2 = d2a; tidx = ia; have_tau = true; }
                 }
-                if (rank == need - 1) { td2 = d2a; tidx = ia; have_tau = true; }
-            }
-            const unsigned who = __ballot_sync(kFull, have_tau);
-            const int src_lane = __ffs(who) - 1;
-            tau_d2 = __shfl_sync(kFull, td2, src_lane);
-            tau_idx = __shfl_sync(kFull, tidx, src_lane);
-        } else {
-            // pathological bucket (many duplicates): extract the `need` smallest keys of the bucket one at a time ...
-            double last_d2 = -1.0;
-            int last_idx = -1;
-            for (int t = 0; t < need; ++t) {
-                double md2 = INFINITY;
-                int midx = 0x7fffffff;
-                for (int cc = 0; cc < ncell; ++cc) {
-                    const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-                    for (unsigned u = cst + lane; u < cen; u += 32) {
+                const unsigned who = __ballot_sync(kFull, have_tau);
+                const int src_lane = __ffs(who) - 1;
+                tau_d2 = __shfl_sync(kFull, td2, src_lane);
+                tau_idx = __shfl_sync(kFull, tidx, src_lane);
+            } else {
+                // pathological bucket (many duplicates): extract the `need` smallest keys of the bucket one at a time ...
+                double last_d2 = -1.0;
+                int last_idx = -1;
+                for (int t = 0; t < need; ++t) {
+                    double md2 = INFINITY;
+                    int midx = 0x7fffffff;
+                    for (int rr = 0; rr < nruns; ++rr) {
+                        const uint2 run = runs[rr];
+                        for (unsigned u = run.x + lane; u < run.y; u += 32) {
+                            double x, y, z;
+                            int idx;
+                            load_rec(recs + u, x, y, z, idx);
+                            const double d2 = sqdist(qx, qy, qz, x, y, z);
+                            if (d2 < rq2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
+                                key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od2 = __shfl_xor_sync(kFull, md2, o);
+                        const int oidx = __shfl_xor_sync(kFull, midx, o);
+                        if (key_less(od2, oidx, md2, midx)) { md2 = od2; midx = oidx; }
+                    }
+                    last_d2 = md2; last_idx = midx;
+                }
+                tau_d2 = last_d2; tau_idx = last_idx;
+                // ... and redo the accumulation with the exact threshold
+                sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0;
+                cnt = 0;
+                for (int rr = 0; rr < nruns; ++rr) {
+                    const uint2 run = runs[rr];
+                    for (unsigned u = run.x + lane; u < run.y; u += 32) {
                         double x, y, z;
                         int idx;
                         load_rec(recs + u, x, y, z, idx);
                         const double d2 = sqdist(qx, qy, qz, x, y, z);
-                        if (d2 < r2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
-                            key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
+                        if (d2 < rq2 && !key_less(tau_d2, tau_idx, d2, idx)) accumulate(x, y, z);
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double od2 = __shfl_xor_sync(kFull, md2, o);
-                    const int oidx = __shfl_xor_sync(kFull, midx, o);
-                    if (key_less(od2, oidx, md2, midx)) { md2 = od2; midx = oidx; }
-                }
-                last_d2 = md2; last_idx = midx;
             }
-            tau_d2 = last_d2; tau_idx = last_idx;
-            // ... and redo the accumulation with the exact threshold
-            sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0;
-            cnt = 0;
-            for (int cc = 0; cc < ncell; ++cc) {
-                const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-                for (unsigned u = cst + lane; u < cen; u += 32) {
-                    double x, y, z;
-                    int idx;
-                    load_rec(recs + u, x, y, z, idx);
-                    const double d2 = sqdist(qx, qy, qz, x, y, z);
-                    if (d2 < r2 && !key_less(tau_d2, tau_idx, d2, idx)) accumulate(x, y, z);
-                }
-            }
+        } else if (trial) {
+            tau_d2 = rq2;      // exactly k points inside the trial radius: all of them, none on the boundary
         }
+        break;
     }
 
+    if (np.debug && lane == 0 && (p % 997) == 0)
+        printf("NRM p=%d total=%d ntry=%d total_try=%d rtry=%.3f used_trial=%d nruns=%d\n", p, total, ntry, total_try, rtry, (int)(runs == runs_try), nruns);
     cnt = warp_sum(cnt);
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
@@ -407,17 +478,17 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         int* order = reinterpret_cast<int*>(wmem + kCanon * 16);
         __syncwarp();
         int m = 0;
-        for (int cc = 0; cc < ncell; ++cc) {
-            const unsigned cst = __shfl_sync(kFull, st, cc), cen = __shfl_sync(kFull, en, cc);
-            for (unsigned t = cst; t < cen; t += 32) {
+        for (int rr = 0; rr < nruns; ++rr) {
+            const uint2 run = runs[rr];
+            for (unsigned t = run.x; t < run.y; t += 32) {
                 const unsigned j = t + lane;
                 double x, y, z, d2 = INFINITY;
                 int idx = 0;
-                if (j < cen) {
+                if (j < run.y) {
                     load_rec(recs + j, x, y, z, idx);
                     d2 = sqdist(qx, qy, qz, x, y, z);
                 }
-                const bool sel = d2 < r2 && !key_less(tau_d2, tau_idx, d2, idx);
+                const bool sel = d2 < rq2 && !key_less(tau_d2, tau_idx, d2, idx);
                 const unsigned msk = __ballot_sync(kFull, sel);
                 if (sel) {
                     const int slot = m + __popc(msk & ((1u << lane) - 1u));
@@ -460,8 +531,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     }
 }
 
-void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow) {
+void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np_in, bool any_wide, bool any_narrow) {
     if (n_scans == 0 || cap_max == 0) return;
+    NormalParams np = np_in;
+    np.r2 = np.radius * np.radius;
+    np.bin_scale = (double)kBins / np.r2;
+    np.r2_lo = (float)(np.r2 * (1.0 - 2e-6));
+    np.r2_hi = (float)(np.r2 * (1.0 + 2e-6));
+    np.bin_scale_f = (float)np.bin_scale;
+    np.debug = getenv("ARVC_DEBUG_NORMALS") ? 1 : 0;
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
     const size_t smem = (size_t)kNrmWarps * kWarpSmem;
     static bool attr_set = false;
