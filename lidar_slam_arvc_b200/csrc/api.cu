@@ -564,11 +564,12 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             int* prev = P.take<int>(cap);
             float* lb2 = P.take<float>(cap);
             unsigned char* cpass = P.take<unsigned char>(cap);
+            int* list = P.take<int>(cap + (cap + 255) / 256 * 8);   // + padding per block of the select kernel
             int* ct = trace ? P.take<int>(cap * passes) : nullptr;
             double* stt = trace ? P.take<double>((size_t)passes * 18) : nullptr;
             if (pass) {
                 hp[i].src = S[i]->d_dev; hp[i].tgt = T[i]->d_dev; hp[i].state = d_states + i;
-                hp[i].partials = partials; hp[i].prev = prev; hp[i].lb2 = lb2; hp[i].cert_pass = cpass; hp[i].corr_trace = ct; hp[i].state_trace = stt;
+                hp[i].partials = partials; hp[i].prev = prev; hp[i].lb2 = lb2; hp[i].cert_pass = cpass; hp[i].list = list; hp[i].corr_trace = ct; hp[i].state_trace = stt;
                 if (trace && d_corr_trace) { *d_corr_trace = ct; *d_state_trace = stt; }
             }
         }
@@ -594,6 +595,8 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             {
                 const char* cm = getenv("ARVC_CERT_MARGIN");      // tuning knob; results do not depend on it
                 ip.cert_margin = cm ? atof(cm) : 0.02;
+                const char* cp = getenv("ARVC_CHUNK_PAIRS");
+                ip.chunk_pairs = cp ? atoi(cp) : 0;
                 ip.debug = getenv("ARVC_DEBUG_STATS") ? atoi(getenv("ARVC_DEBUG_STATS")) : 0;
             }
             run_icp(ctx->L, d_pairs, n_pairs, src_cap_max, ip, combos);
@@ -617,8 +620,14 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
         unsigned long long tot[8] = {0};
         long long passes = 0;
         for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 8; ++k) tot[k] += pb.h_states[i].dbg[k]; passes += pb.h_states[i].passes; }
-        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu skipped_by_certificate=%llu union=%llu fallback=%llu (start level 2:%llu 3:%llu 4:%llu 5+:%llu)\n", pb.n_pairs, passes,
-                tot[3], tot[0], tot[1], tot[2], tot[4], tot[5], tot[6], tot[7]);
+        if (atoi(getenv("ARVC_DEBUG_STATS")) & 8) {
+            unsigned long long mx = 0;
+            for (int i = 0; i < pb.n_pairs; ++i) mx = std::max(mx, (unsigned long long)pb.h_states[i].dbg[0]);
+            fprintf(stderr, "[arvc warp-time] warm-pass search warps by duration: <10us:%llu <20:%llu <40:%llu <80:%llu <160:%llu <320:%llu >=320:%llu  max=%.0f us\n",
+                    tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], tot[7], (double)mx / 1965.0);
+        }
+        fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu searched=%llu (union=%llu fallback=%llu)\n", pb.n_pairs, passes,
+                tot[3], tot[0], tot[1], tot[2]);
     }
     for (int i = 0; i < pb.n_pairs; ++i) {
         const PairState& st = pb.h_states[i];

@@ -65,7 +65,8 @@ struct __align__(16) PairState {
     int done;
     int ncorr;
     int err;                // OR of the two scans' device error flags
-    int pad[3];
+    int nlist;              // entries of the work list of the current pass
+    int pad[2];
     unsigned long long dbg[8];   // search statistics (ARVC_DEBUG_STATS): skipped / union / fallback queries, queries, fallback by level
     // ---- device-only tail (not copied back): top three rows of the transformation each pass was evaluated at
     double Thist[12 * kThist];
@@ -80,6 +81,7 @@ struct PairDev {
     int* prev;              // [src cap] Morton position of last pass' match in the target, or -1
     float* lb2;             // [src cap] certificate: lower bound on the distance to every other target point ...
     unsigned char* cert_pass;   // [src cap] ... at the pass it was established (255 = none)
+    int* list;              // [src cap] source points whose nearest neighbour has to be searched in this pass
     int* corr_trace;        // optional [(max_iter+1)][src cap] (cloud order), may be null
     double* state_trace;    // optional [(max_iter+1)][18]: T16, fitness, rmse
 };
@@ -92,7 +94,7 @@ struct IcpParams {
     int max_iter;
     int method;
     int debug;              // collect search statistics into PairState (ARVC_DEBUG_STATS)
-    int pad;
+    int chunk_pairs;        // pairs iterated together (0 = whole batch)
 };
 
 constexpr int kSumStride = 32;

@@ -35,6 +35,7 @@ constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
 constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may hold
+constexpr int kUnionScanCap = 384;    // larger unions are split per query (lanes share the records of one query)
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
 
@@ -115,16 +116,29 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
             const int el = (int)en4.w;
             const unsigned cnt = en4.y - en4.x;
             if (el == 0 || cnt <= (unsigned)kBigRun || top + 8 > kStack) {
-                for (unsigned p = en4.x + gl; p < en4.y; p += kG) {
-                    if constexpr (!TW) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(recs + p));
-                        const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
-                        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        if (d2f <= thr) {
-                            const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
-                            const int idx = __float_as_int(v.w);
-                            if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; thr = screen_thr(d2, e); }
+                if constexpr (!TW) {
+                    for (unsigned p0 = en4.x + gl; p0 < en4.y; p0 += 4 * kG) {      // four loads in flight per lane
+                        float4 v4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const unsigned p = p0 + u * kG;
+                            v4[u] = p < en4.y ? __ldg(reinterpret_cast<const float4*>(recs + p)) : make_float4(INFINITY, 0.f, 0.f, 0.f);
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 v = v4[u];
+                            const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                            const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (d2f <= thr) {
+                                const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                                const int idx = __float_as_int(v.w);
+                                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); thr = screen_thr(d2, e); }
+                            }
+                        }
+                    }
+                }
+                for (unsigned p = en4.x + gl; TW && p < en4.y; p += kG) {
+                    if constexpr (!TW) {
                     } else {
                         double x, y, z;
                         int idx;
@@ -319,11 +333,75 @@ __device__ void solve_update(int method, const double* S, double* upd) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
-// Pass kernel: one thread per source point (Morton order), kIcpBlock threads per block, no block-level barrier
-// after the prologue - warps are independent and write one row of partial sums each.
+// One ICP pass = three kernels + the per-pair finish kernel, all over the whole batch:
+//   k_icp_select  (passes > 0) per source point: distance to the previous match and certificate test; points
+//                 whose nearest neighbour is not certified are appended to the pair's work list;
+//   k_icp_search  exact nearest-neighbour search for the listed points only (every point in pass 0), 8 consecutive
+//                 list entries per group, so the cost follows the number of uncertified points;
+//   k_icp_accum   per source point in Morton order: residual / Jacobian or Umeyama moments of its match, fixed-order
+//                 warp reduction into one row of partial sums per warp (bit-reproducible run to run).
 // ---------------------------------------------------------------------------------------------------
-template <int METHOD, bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+template <bool SW, bool TW>
+__global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+    typedef typename RecT<SW>::type SRec;
+    typedef typename RecT<TW>::type TRec;
+    const PairDev& pr = pairs[blockIdx.y];
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
+    PairState* st = pr.state;
+    if (st->done) return;
+    const int n = src.counts[CNT_NPTS];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (i < n) {
+        double px, py, pz;
+        int sidx;
+        load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
+        const double* T = st->T;
+        const double sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
+        const double sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+        const double sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+        need = (sx == sx && sy == sy && sz == sz) && ip.max_d2 > 0;
+        const int pv = pr.prev[i];
+        const int c = pr.cert_pass[i];
+        if (need && pv >= 0 && c != 255) {
+            // Certificate from pass c: every other target point was at least lb2 away from this source point's position
+            // then.  It has moved by delta since, so every other point is still at least lb2 - delta away: if the previous
+            // match is strictly closer (and inside the cut-off), it is the unique nearest neighbour - no search.
+            double x, y, z;
+            int idx;
+            load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pv, x, y, z, idx);
+            const double d2 = sqdist(sx, sy, sz, x, y, z);
+            const double* Tc = st->Thist + 12 * c;
+            const double ex = sx - (Tc[0] * px + Tc[1] * py + Tc[2] * pz + Tc[3]);
+            const double ey = sy - (Tc[4] * px + Tc[5] * py + Tc[6] * pz + Tc[7]);
+            const double ez = sz - (Tc[8] * px + Tc[9] * py + Tc[10] * pz + Tc[11]);
+            const double delta = sqrt(ex * ex + ey * ey + ez * ez);
+            const double br = sqrt(d2) * (1.0 + 1e-9) + 1e-12;
+            if (d2 < ip.max_d2 && (br + delta) * (1.0 + 1e-7) + 1e-9 < (double)pr.lb2[i]) need = false;
+        }
+    }
+    // block-ordered append, padded to a multiple of kG with -1: the kG entries a search group serves then always come
+    // from one block of 256 consecutive (Morton-sorted) source points, which keeps the groups spatially compact
+    __shared__ int s_cnt[8], s_base;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(kFull, need);
+    if (lane == 0) s_cnt[w] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { before += k < w ? s_cnt[k] : 0; total += s_cnt[k]; }
+    const int padded = (total + kG - 1) / kG * kG;
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(&st->nlist, padded) : 0;
+    __syncthreads();
+    if (need) pr.list[s_base + before + __popc(m & ((1u << lane) - 1u))] = i;
+    if ((int)threadIdx.x < padded - total) pr.list[s_base + total + threadIdx.x] = -1;
+}
+
+template <bool SW, bool TW>
+__global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
@@ -337,26 +415,28 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
     if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
-    const int n = src.counts[CNT_NPTS];
-    const int nblk = max(1, (n + kIcpBlock - 1) / kIcpBlock);
-    if ((int)blockIdx.x >= nblk) return;
+    const int n = pass == 0 ? src.counts[CNT_NPTS] : st->nlist;       // pass 0 searches every point
+    if ((int)(blockIdx.x * kIcpBlock) >= n) return;
+    const long long t_begin = clock64();
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
     const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
     double T[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->T[k];
 
-    const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+    const int t_idx = blockIdx.x * kIcpBlock + threadIdx.x;
+    const int i = t_idx < n ? (pass == 0 ? t_idx : pr.list[t_idx]) : -1;      // -1: padding entry
     // ---- per lane: transform the source point, bound the search with the previous pass' match
     double sx = 0, sy = 0, sz = 0;
-    int sidx = 0, level = 0;
+    int level = 0;
     bool active = false, certified = true;
     float cert_lb = 0.f;                 // new certificate (0 = none)
     Best b;
     b.d2 = ip.max_d2; b.idx = -1; b.pos = -1;
-    int stat_skip = 0, stat_union = 0, stat_fb = 0;
-    if (i < n) {
+    int stat_union = 0, stat_fb = 0;
+    if (i >= 0) {
         double px, py, pz;
+        int sidx;
         load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
         sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
         sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
@@ -376,18 +456,6 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                     b.d2 = d2; b.idx = idx; b.pos = pv;
                     const double br = sqrt(d2) * (1.0 + 1e-9) + 1e-12;
                     while (level < g.top_level && g.c0 * (double)(1 << level) < br) ++level;
-                    // Certificate from an earlier pass c: every other target point was at least lb2 away from this
-                    // source point's position then.  It moved by delta since, so every other point is still at least
-                    // lb2 - delta away: if the previous match is strictly closer, it is the unique nearest neighbour.
-                    const int c = pr.cert_pass[i];
-                    if (c != 255) {
-                        const double* Tc = st->Thist + 12 * c;
-                        const double ex = sx - (Tc[0] * px + Tc[1] * py + Tc[2] * pz + Tc[3]);
-                        const double ey = sy - (Tc[4] * px + Tc[5] * py + Tc[6] * pz + Tc[7]);
-                        const double ez = sz - (Tc[8] * px + Tc[9] * py + Tc[10] * pz + Tc[11]);
-                        const double delta = sqrt(ex * ex + ey * ey + ez * ez);
-                        if ((br + delta) * (1.0 + 1e-7) + 1e-9 < (double)pr.lb2[i]) { certified = true; cert_lb = -1.f; ++stat_skip; }
-                    }
                 }
             }
         }
@@ -400,7 +468,8 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
     {
         const GridSpec g = tgt.grid;
         const TRec* __restrict__ trecs = reinterpret_cast<const TRec*>(tgt.recs);
-        uint2* runs = reinterpret_cast<uint2*>(s_stk[grp]);          // kStack * 16 bytes = 2 * kStack runs
+        uint2* runs = reinterpret_cast<uint2*>(s_stk[grp]);          // kStack * 16 bytes: kUnionMax runs (8 B) ...
+        unsigned* rcell = reinterpret_cast<unsigned*>(runs + kUnionMax);   // ... + their cell offsets (4 B)
         const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
         const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
         float thr = screen_thr(b.d2, e);
@@ -436,7 +505,11 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
                     valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(cx, cy, cz), rs, re);
                 }
                 const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
-                if (valid) runs[nr + __popc(vm & ((1u << gl) - 1u))] = make_uint2(rs, re);
+                if (valid) {
+                    const int slot = nr + __popc(vm & ((1u << gl) - 1u));
+                    runs[slot] = make_uint2(rs, re);
+                    rcell[slot] = (unsigned)(t % nx) | ((unsigned)((t / nx) % ny) << 8) | ((unsigned)(t / (nx * ny)) << 16);   // offsets from x0,y0,z0
+                }
                 nr += __popc(vm);
                 utotal += (int)(re - rs);
             }
@@ -444,8 +517,68 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             for (int o = kG / 2; o > 0; o >>= 1) utotal += __shfl_xor_sync(gmask, utotal, o, kG);
             __syncwarp(gmask);
             // coarse levels pay off only where the scan is sparse; dense unions are left to the per-query search
-            if (lu >= 2 && utotal > kUnionCandCap) { if ((ip.debug & 1) && want) atomicAdd(&pr.state->dbg[7], 1ull); break; }
+            if (lu >= 2 && utotal > kUnionCandCap) break;
             float f1 = INFINITY, f2 = INFINITY;     // two smallest screened float32 distances (multiset)
+            if (!TW && utotal > kUnionScanCap) {
+                // Dense union: every lane screening every record would cost lanes x records.  Serve the wanting lanes one
+                // at a time instead: the 8 lanes split the records of the cells that touch that lane's own ball (the
+                // union's run table is reused, no further lookups), then agree on the (d2, index) minimum.
+                const float4* __restrict__ tr4 = reinterpret_cast<const float4*>(trecs);
+                for (int k = 0; k < kG; ++k) {
+                    if (!__shfl_sync(gmask, (int)want, k, kG)) continue;
+                    const double qx = __shfl_sync(gmask, sx, k, kG), qy = __shfl_sync(gmask, sy, k, kG), qz = __shfl_sync(gmask, sz, k, kG);
+                    const double qr = __shfl_sync(gmask, r, k, kG);
+                    Best lb;
+                    lb.d2 = __shfl_sync(gmask, b.d2, k, kG); lb.idx = __shfl_sync(gmask, b.idx, k, kG); lb.pos = -1;
+                    const int kx0 = (cell_coord(qx - qr, g.ox, g.inv_c0) >> lu) - x0, kx1 = (cell_coord(qx + qr, g.ox, g.inv_c0) >> lu) - x0;
+                    const int ky0 = (cell_coord(qy - qr, g.oy, g.inv_c0) >> lu) - y0, ky1 = (cell_coord(qy + qr, g.oy, g.inv_c0) >> lu) - y0;
+                    const int kz0 = (cell_coord(qz - qr, g.oz, g.inv_c0) >> lu) - z0, kz1 = (cell_coord(qz + qr, g.oz, g.inv_c0) >> lu) - z0;
+                    const float qxf = (float)qx, qyf = (float)qy, qzf = (float)qz;
+                    const float qe = (float)(fmax(fabs(qx), fmax(fabs(qy), fabs(qz))) * 6.0e-8 + 1e-30);
+                    float qthr = screen_thr(lb.d2, qe), g1 = INFINITY, g2 = INFINITY;
+                    for (int rr = 0; rr < nr; ++rr) {
+                        const unsigned rc = rcell[rr];
+                        const int ox = (int)(rc & 255u), oy = (int)((rc >> 8) & 255u), oz = (int)(rc >> 16);
+                        if (ox < kx0 || ox > kx1 || oy < ky0 || oy > ky1 || oz < kz0 || oz > kz1) continue;
+                        const uint2 run = runs[rr];
+                        for (unsigned p0 = run.x + gl; p0 < run.y; p0 += 4 * kG) {      // four loads in flight per lane
+                            float4 v4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const unsigned p = p0 + u * kG;
+                                v4[u] = p < run.y ? __ldg(tr4 + p) : make_float4(INFINITY, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 v = v4[u];
+                                const float dx = qxf - v.x, dy = qyf - v.y, dz = qzf - v.z;
+                                const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));     // +inf for the padding lanes
+                                g2 = fminf(g2, fmaxf(g1, d2f));
+                                g1 = fminf(g1, d2f);
+                                if (d2f <= qthr) {
+                                    const double d2 = sqdist(qx, qy, qz, (double)v.x, (double)v.y, (double)v.z);
+                                    const int idx = __float_as_int(v.w);
+                                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); qthr = screen_thr(d2, qe); }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = kG / 2; o > 0; o >>= 1) {
+                        const double od2 = __shfl_xor_sync(gmask, lb.d2, o, kG);
+                        const int oidx = __shfl_xor_sync(gmask, lb.idx, o, kG);
+                        const int opos = __shfl_xor_sync(gmask, lb.pos, o, kG);
+                        if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
+                        const float h1 = __shfl_xor_sync(gmask, g1, o, kG), h2 = __shfl_xor_sync(gmask, g2, o, kG);
+                        g2 = fminf(fmaxf(g1, h1), fminf(g2, h2));      // two smallest of the merged multisets
+                        g1 = fminf(g1, h1);
+                    }
+                    if (gl == k) {
+                        if (lb.pos >= 0) b = lb;
+                        f1 = g1; f2 = g2;
+                    }
+                }
+            } else
             if constexpr (!TW) {
                 float4* stage = s_stage[grp];
                 int* spos = s_spos[grp];
@@ -511,6 +644,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             }
         }
     }
+    const long long t_union_end = clock64();
     // ---- remaining queries (nearest neighbour beyond the union levels): the warp's pending queries are dealt round
     // robin to its 32/kG groups, each group serving one query at a time with the cooperative branch-and-bound search
     {
@@ -538,59 +672,94 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_pass(const PairDev* __restric
             if (mine) {
                 if (rpos >= 0) { b.d2 = rd2; b.idx = ridx; b.pos = rpos; }
                 ++stat_fb;
-                if (ip.debug & 1) atomicAdd(&pr.state->dbg[4 + min(max(level - 2, 0), 3)], 1ull);
             }
         }
     }
 
-    // ---- per lane: residual / Jacobian (point-to-plane) or Umeyama moments (point-to-point)
+    if (i >= 0) {
+        pr.prev[i] = b.pos;
+        const bool ok = cert_lb > 0.f && pass < kThist;
+        pr.cert_pass[i] = ok ? (unsigned char)pass : (unsigned char)255;
+        if (ok) pr.lb2[i] = cert_lb;
+    }
+    if ((ip.debug & 8) && lane == 0 && pass > 0) {
+        const long long dt = clock64() - t_begin;
+        int bkt = 0;
+        while (bkt < 6 && dt > (20000ll << bkt)) ++bkt;      // 20k cycles ~ 10 us, doubling
+        atomicAdd(&pr.state->dbg[1 + bkt], 1ull);
+        atomicMax(&pr.state->dbg[0], (unsigned long long)dt);
+        if (dt > 400000) printf("SLOW warp pass=%d pair=%d blk=%d total=%.0fus union=%.0fus fallback=%.0fus\n", pass, (int)blockIdx.y, (int)blockIdx.x, dt / 1965.0, (t_union_end - t_begin) / 1965.0, (clock64() - t_union_end) / 1965.0);
+    }
+    if (ip.debug & 1) {
+        const int u = warp_sum(stat_union), f = warp_sum(stat_fb), ac = warp_sum(i >= 0 ? 1 : 0);
+        if (lane == 0) { atomicAdd(&pr.state->dbg[0], (unsigned long long)ac); atomicAdd(&pr.state->dbg[1], (unsigned long long)u);
+                         atomicAdd(&pr.state->dbg[2], (unsigned long long)f); }
+    }
+}
+
+template <int METHOD, bool SW, bool TW>
+__global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+    typedef typename RecT<SW>::type SRec;
+    typedef typename RecT<TW>::type TRec;
+    const PairDev& pr = pairs[blockIdx.y];
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
+    const PairState* __restrict__ st = pr.state;
+    if (st->done) return;
+    const int n = src.counts[CNT_NPTS];
+    const int nblk = max(1, (n + kIcpBlock - 1) / kIcpBlock);
+    if ((int)blockIdx.x >= nblk) return;
+    const int lane = lane_id();
+    const int i = blockIdx.x * kIcpBlock + threadIdx.x;
     double acc[kNS];
 #pragma unroll
     for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
     if (i < n) {
-        pr.prev[i] = b.pos;
-        if (cert_lb >= 0.f) {      // < 0: an older certificate was used and stays valid
-            const bool ok = cert_lb > 0.f && pass < kThist;
-            pr.cert_pass[i] = ok ? (unsigned char)pass : (unsigned char)255;
-            if (ok) pr.lb2[i] = cert_lb;
-        }
-        if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = b.pos >= 0 ? b.idx : -1;
-        if (b.pos >= 0) {
-            double tx, ty, tz;
-            int tidx;
-            load_rec(reinterpret_cast<const TRec*>(tgt.recs) + b.pos, tx, ty, tz, tidx);
-            acc[27] = b.d2;
-            acc[28] = 1.0;
-            if (METHOD == 1) {
-                const double4 nv = reinterpret_cast<const double4*>(tgt.normals)[b.pos];
-                const double r = (sx - tx) * nv.x + (sy - ty) * nv.y + (sz - tz) * nv.z;
-                const double J[6] = {sy * nv.z - sz * nv.y, sz * nv.x - sx * nv.z, sx * nv.y - sy * nv.x, nv.x, nv.y, nv.z};
-                int t = 0;
+        const int pos = pr.prev[i];
+        int sidx = 0;
+        if (pos >= 0 || pr.corr_trace) {
+            double px, py, pz;
+            load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
+            if (pos >= 0) {
+                const double* T = st->T;
+                const double sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
+                const double sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+                const double sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+                double tx, ty, tz;
+                int tidx;
+                load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pos, tx, ty, tz, tidx);
+                acc[27] = sqdist(sx, sy, sz, tx, ty, tz);
+                acc[28] = 1.0;
+                if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = tidx;
+                if (METHOD == 1) {
+                    const double4 nv = reinterpret_cast<const double4*>(tgt.normals)[pos];
+                    const double r = (sx - tx) * nv.x + (sy - ty) * nv.y + (sz - tz) * nv.z;
+                    const double J[6] = {sy * nv.z - sz * nv.y, sz * nv.x - sx * nv.z, sx * nv.y - sy * nv.x, nv.x, nv.y, nv.z};
+                    int t = 0;
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
+                    for (int a = 0; a < 6; ++a)
 #pragma unroll
-                    for (int c = a; c < 6; ++c) acc[t++] = J[a] * J[c];
+                        for (int c = a; c < 6; ++c) acc[t++] = J[a] * J[c];
 #pragma unroll
-                for (int a = 0; a < 6; ++a) acc[21 + a] = J[a] * r;
+                    for (int a = 0; a < 6; ++a) acc[21 + a] = J[a] * r;
+                } else {
+                    acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
+                    acc[6] = tx * sx; acc[7] = tx * sy; acc[8] = tx * sz;
+                    acc[9] = ty * sx; acc[10] = ty * sy; acc[11] = ty * sz;
+                    acc[12] = tz * sx; acc[13] = tz * sy; acc[14] = tz * sz;
+                }
             } else {
-                acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
-                acc[6] = tx * sx; acc[7] = tx * sy; acc[8] = tx * sz;
-                acc[9] = ty * sx; acc[10] = ty * sy; acc[11] = ty * sz;
-                acc[12] = tz * sx; acc[13] = tz * sy; acc[14] = tz * sz;
+                pr.corr_trace[(size_t)pass * src.cap + sidx] = -1;
             }
         }
     }
-    // warp reduction in a fixed order; one row of partial sums per warp (bit-reproducible run to run)
     double* row = pr.partials + ((size_t)blockIdx.x * (kIcpBlock / 32) + (threadIdx.x >> 5)) * kSumStride;
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         if (METHOD == 0 && k >= 15 && k < 27) continue;
         const double v = warp_sum(acc[k]);
         if (lane == 0) row[k] = v;
-    }
-    if (ip.debug & 1) {
-        const int a = warp_sum(stat_skip), u = warp_sum(stat_union), f = warp_sum(stat_fb);
-        if (lane == 0) { row[29] = (double)a; row[30] = (double)u; row[31] = (double)f; }
     }
 }
 
@@ -635,7 +804,8 @@ __global__ void __launch_bounds__(256) k_icp_finish(const PairDev* __restrict__ 
         st->ncorr = (int)K;
         st->passes = pass + 1;
         for (int k = 0; k < kNS; ++k) st->sums[k] = s_sum[k];
-        if (ip.debug & 1) { st->dbg[0] += (unsigned long long)s_sum[29]; st->dbg[1] += (unsigned long long)s_sum[30]; st->dbg[2] += (unsigned long long)s_sum[31]; st->dbg[3] += (unsigned long long)n; }
+        if (ip.debug & 1) st->dbg[3] += (unsigned long long)n;
+        st->nlist = 0;
         if (stop) {
             st->done = 1;
         } else {
@@ -661,22 +831,39 @@ static const char* pass_name(int pass) {   // "icp_pass_00" ... so that the prof
 }
 
 template <int METHOD>
-static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, const IcpParams& ip, int pass, int combos_mask) {
+static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, int cap_max, const IcpParams& ip, int pass, int combos_mask) {
     const char* nm = pass_name(pass);
-    if (combos_mask & 1) L.launch(nm, k_icp_pass<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch(nm, k_icp_pass<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch(nm, k_icp_pass<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch(nm, k_icp_pass<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    const dim3 g256((cap_max + 255) / 256, grid.y);
+    if (pass > 0) {
+        if (combos_mask & 1) L.launch("icp_select", k_icp_select<false, false>, g256, dim3(256), d_pairs, ip, pass);
+        if (combos_mask & 2) L.launch("icp_select", k_icp_select<false, true>, g256, dim3(256), d_pairs, ip, pass);
+        if (combos_mask & 4) L.launch("icp_select", k_icp_select<true, false>, g256, dim3(256), d_pairs, ip, pass);
+        if (combos_mask & 8) L.launch("icp_select", k_icp_select<true, true>, g256, dim3(256), d_pairs, ip, pass);
+    }
+    if (combos_mask & 1) L.launch(nm, k_icp_search<false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 2) L.launch(nm, k_icp_search<false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 4) L.launch(nm, k_icp_search<true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 8) L.launch(nm, k_icp_search<true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 1) L.launch("icp_accum", k_icp_accum<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 2) L.launch("icp_accum", k_icp_accum<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 4) L.launch("icp_accum", k_icp_accum<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 8) L.launch("icp_accum", k_icp_accum<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
     L.launch("icp_finish", k_icp_finish<METHOD>, dim3(grid.y), dim3(256), d_pairs, ip, pass);
 }
 
 // combos_mask bit (2*src_wide + tgt_wide) set when some pair of the batch has that record-type combination
 void run_icp(Launcher& L, const PairDev* d_pairs, int n_pairs, int src_cap_max, const IcpParams& ip, int combos_mask) {
     if (n_pairs == 0) return;
-    const dim3 grid(max(1, (src_cap_max + kIcpBlock - 1) / kIcpBlock), n_pairs);
-    for (int pass = 0; pass <= ip.max_iter; ++pass) {
-        if (ip.method == 1) launch_combos<1>(L, d_pairs, grid, ip, pass, combos_mask);
-        else launch_combos<0>(L, d_pairs, grid, ip, pass, combos_mask);
+    // Pairs are iterated in chunks small enough for their scans, grids and normals (~8 MB per pair) to stay L2
+    // resident between consecutive passes; a batch-wide pass would stream the whole batch through L2 every pass.
+    const int chunk = ip.chunk_pairs > 0 ? ip.chunk_pairs : n_pairs;
+    for (int c0 = 0; c0 < n_pairs; c0 += chunk) {
+        const int nc = min(chunk, n_pairs - c0);
+        const dim3 grid(max(1, (src_cap_max + kIcpBlock - 1) / kIcpBlock), nc);
+        for (int pass = 0; pass <= ip.max_iter; ++pass) {
+            if (ip.method == 1) launch_combos<1>(L, d_pairs + c0, grid, src_cap_max, ip, pass, combos_mask);
+            else launch_combos<0>(L, d_pairs + c0, grid, src_cap_max, ip, pass, combos_mask);
+        }
     }
 }
 
