@@ -120,7 +120,7 @@ constexpr int kCanon = 320;          // most neighbours the canonical (sorted, s
 constexpr int kScratch = kCanon * 20;  // bytes of the two overlapping layouts above
 constexpr int kTryRuns = 160;          // cells of the trial ball (6^3 = 216 before box pruning)
 constexpr int kWarpSmem = kScratch + (64 + kTryRuns) * 8;   // + cell runs, which outlive both layouts
-constexpr int kDenseFactor = 3;        // neighbourhoods with more than kDenseFactor * max_nn candidates try a smaller radius first
+constexpr int kDenseFactor2 = 3;       // neighbourhoods with more than kDenseFactor2/2 * max_nn candidates try a smaller radius first
 static_assert(kBins * 4 + kCand * 16 <= kScratch, "selection layout must fit");
 constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
 
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     // let the histogram pass verify the guess: if it holds fewer than k points, fall back to the full radius.
     int ntry = 0, total_try = 0;
     double rtry = 0.0;
-    if (total > kDenseFactor * np.max_nn && L > 0) {
-        rtry = 1.35 * 3.0 * cl * sqrt((double)np.max_nn / (3.141592653589793 * (double)total));
-        if (rtry < 0.8 * np.radius) {
+    if (2 * total > kDenseFactor2 * np.max_nn && L > 0) {
+        rtry = 1.1 * 3.0 * cl * sqrt((double)np.max_nn / (3.141592653589793 * (double)total));     // 10 % safety on the density model
+        if (rtry < 0.95 * np.radius) {
             const int Lf = L - 1;
             const double cf = 0.5 * cl, rt = rtry * (1.0 + 1e-9) + 1e-12, rt2 = rtry * rtry;
             const int fx0 = cell_coord(qx - rt, g.ox, g.inv_c0) >> Lf, fx1 = cell_coord(qx + rt, g.ox, g.inv_c0) >> Lf;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         break;
     }
 
-    if (np.debug && lane == 0 && (p % 997) == 0)
+    if (np.debug && lane == 0 && (p % 997) == 0)      // ARVC_DEBUG_NORMALS=1: sampled per-point search statistics
         printf("NRM p=%d total=%d ntry=%d total_try=%d rtry=%.3f used_trial=%d nruns=%d\n", p, total, ntry, total_try, rtry, (int)(runs == runs_try), nruns);
     cnt = warp_sum(cnt);
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
