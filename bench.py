@@ -291,8 +291,12 @@ def main():
     achieved = alg_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(name)
+    if os.path.exists(tpath) and n_launch:      # DRAM bytes per unit from the committed ncu --set full capture, scaled to this launch
+        tj = json.load(open(tpath))
+        if name == "normals" and "normals" in tj:
+            traffic = tj["normals"]["dram_bytes_per_scan"] * len(ids)
+        elif name == "icp_pass" and "icp_pass" in tj:
+            traffic = tj["icp_pass"]["dram_bytes_per_pair_pass"] * float(sum(int(x) for x in own["passes"])) * args.steps / n_launch
     roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launches": n_launch, "kernel_ms_total": tot_ms,
                 "kernel_share_of_device_time": tot_ms / dev_ms if dev_ms > 0 else None,
