@@ -279,3 +279,63 @@ def test_full_size_64_beam_pair(eng):
     assert_transform_close(tr["result"]["T"], ref.transformation)
     assert_rel(tr["result"]["fitness"], ref.fitness)
     assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs 2-4 shapes
+def test_128_beam_point_to_point_pair(eng):
+    """BASELINE config 3 shape: 128-beam (~260k points) point-to-point pair against the oracle."""
+    seq = synth.Sequence(2, synth.OS_128, start=30.0)
+    tr, ref, src, tgt, _ = _run_pair(eng, seq, 0, 1, engine.P2P)
+    assert len(src) > 200000
+    for k in (0, tr["passes"] - 1):
+        corr, _, fit, _ = orc.correspondences(src, tgt, tr["T"][k], 10.0)
+        np.testing.assert_array_equal(tr["corr"][k], corr)
+        assert tr["fitness"][k] == fit
+    assert tr["result"]["passes"] == ref.passes
+    assert_transform_close(tr["result"]["T"], ref.transformation)
+    assert_rel(tr["result"]["fitness"], ref.fitness)
+    assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
+    eng.free(0)
+    eng.free(1)
+
+
+def test_loop_closure_batch_properties(eng):
+    """BASELINE config 4 shape (scaled down): loop-closure pairs with perturbed initial guesses, one batch.
+    Size-independent properties: a sample agrees with the oracle; a pair's result is independent of the rest of the
+    batch and of its position in it; sharding the batch does not change any result."""
+    from lidar_slam_arvc_b200 import sharding
+    seq = synth.Sequence(24, synth.SMALL_32, start=0.0, step=1.0)
+    pairs = synth.loop_closure_pairs(seq.poses, 40, radius=5.0, min_gap=3, seed=777, sigma_t=0.1, sigma_rot_deg=1.0)
+    assert len(pairs) == 40
+    for k in range(len(seq.scans)):
+        eng.upload(100 + k, seq.scans[k])
+    eng.preprocess([100 + k for k in range(len(seq.scans))], eng.make_preprocess_params())
+    order = sharding.sort_pairs_for_cache([p[0] for p in pairs], [p[1] for p in pairs])
+    tg = np.array([100 + pairs[k][0] for k in order])
+    sr = np.array([100 + pairs[k][1] for k in order])
+    init = np.array([pairs[k][2] for k in order])
+    ip = eng.make_icp_params(engine.P2PLANE)
+    res = eng.icp_batch(tg, sr, init, ip)
+    assert (res["fitness"] > 0.9).all() and (res["updates"] <= 30).all()
+    # oracle on a sample
+    for k in (0, 7, 23, 39):
+        tgt, tn = eng.get_points(int(tg[k]), normals=True)
+        ref = orc.icp(eng.get_points(int(sr[k])), tgt, orc.estimate_normals(tgt), init[k], orc.P2PLANE)
+        assert res["updates"][k] == ref.updates
+        assert_transform_close(res["T"][k], ref.transformation)
+        assert_rel(res["rmse"][k], ref.inlier_rmse)
+    # a pair's result does not depend on what else is in the batch or on its position in it
+    perm = np.random.default_rng(5).permutation(len(tg))
+    shuffled = eng.icp_batch(tg[perm], sr[perm], init[perm], ip)
+    np.testing.assert_array_equal(shuffled["T"], res["T"][perm])
+    np.testing.assert_array_equal(shuffled["updates"], res["updates"][perm])
+    # sharding: two "ranks" process contiguous halves; concatenation equals the single batch bit for bit
+    parts = []
+    for r in range(2):
+        lo, hi = sharding.shard_bounds(len(tg), 2, r)
+        parts.append(eng.icp_batch(tg[lo:hi], sr[lo:hi], init[lo:hi], ip))
+    merged = np.concatenate(parts)
+    np.testing.assert_array_equal(merged["T"], res["T"])
+    np.testing.assert_array_equal(merged["rmse"], res["rmse"])
+    for k in range(len(seq.scans)):
+        eng.free(100 + k)
