@@ -474,12 +474,16 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
         const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
         float thr = screen_thr(b.d2, e);
         const int gshift = lane & ~(kG - 1);
-        for (int lu = 0; lu <= min(kUnionLevels - 1, g.top_level); ++lu) {
-            const bool want = active && !certified && level <= lu;
+        // step -1 (queries without any bound, i.e. the cold pass): look only into the finest cell holding the query; whatever
+        // is found there bounds the real search, whose ball then touches a few cells instead of the full 3x3x3 block
+        for (int step = -1; step <= min(kUnionLevels - 1, g.top_level); ++step) {
+            const int lu = max(step, 0);
+            const bool probe = step < 0;
+            const bool want = active && !certified && (probe ? (b.pos < 0 && level == 0) : level <= lu);
             if (!__any_sync(gmask, want) || (ip.debug & 4)) continue;
             const double cl = g.c0 * (double)(1 << lu);
             // cells are selected for a ball slightly larger than needed: the margin is what later certificates live on
-            const double r = fmin((double)(sqrtf(__double2float_ru(b.d2)) * (1.0f + 1e-6f)) + 1e-12 + ip.cert_margin, cl);
+            const double r = probe ? 1e-9 : fmin((double)(sqrtf(__double2float_ru(b.d2)) * (1.0f + 1e-6f)) + 1e-12 + ip.cert_margin, cl);
             int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1, z0 = 1 << 30, z1 = -1;
             if (want) {
                 x0 = cell_coord(sx - r, g.ox, g.inv_c0) >> lu; x1 = cell_coord(sx + r, g.ox, g.inv_c0) >> lu;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                 }
             }
             __syncwarp(gmask);
-            if (want) {
+            if (want && !probe) {
                 // every target point within min(previous bound, cl) of this lane's query was screened
                 if (sqrt(b.d2) * (1.0 + 1e-9) + 1e-12 <= cl) {
                     certified = true;
