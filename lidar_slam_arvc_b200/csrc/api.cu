@@ -174,6 +174,8 @@ void plan_scratch(SlabPlanner& P, ScanDev& d, int n_raw, bool voxel_on) {
     d.hist = P.take<int>(256 * ((cap + 2047) / 2048));
     d.blk = P.take<int>((cap + 1023) / 1024 + 8);
     d.bbox = P.take<double>(8);
+    d.moments = P.take<double>(cap * 10);
+    d.redo_list = P.take<int>(cap);
 }
 
 __global__ void k_clear_scan(const ScanDev* __restrict__ scans) {

@@ -91,7 +91,7 @@ __device__ __forceinline__ bool grid_lookup(const HashEntry* __restrict__ tab, u
 }
 
 // ---- per-scan device view ------------------------------------------------------------------------------
-enum { CNT_NFILT = 0, CNT_NPTS = 1, CNT_ERR = 2, CNT_NCELLS = 3, CNT_WORDS = 8 };
+enum { CNT_NFILT = 0, CNT_NPTS = 1, CNT_ERR = 2, CNT_NCELLS = 3, CNT_NREDO = 4, CNT_WORDS = 8 };
 enum { ERR_HASH_FULL = 1, ERR_VOXEL_RANGE = 2 };
 
 struct ScanDev {
@@ -121,6 +121,8 @@ struct ScanDev {
     int* hist;              // [256][nblk]
     int* blk;               // [nblk1024 + 8] block counters
     double* bbox;           // [8] min bound / origin of the voxel grid
+    double* moments;        // [cap][10] centred moment sums + neighbour count per point (normals)
+    int* redo_list;         // [cap] points whose normal needs the canonical re-summation
 };
 
 // ---- warp helpers ------------------------------------------------------------------------------------------

@@ -165,15 +165,23 @@ template <> struct CandEval<true> {
     __device__ __forceinline__ int below(float, float) const { return 0; }
 };
 
+// mode 0: neighbour search + selection for every point; the warp stores the centred moment sums and leaves the
+//         eigen-solve to k_normals_eigen (one THREAD per point - the solve is scalar work);
+// mode 1: only the points k_normals_eigen flagged as ill-conditioned: same search, then the canonical re-summation
+//         and the solve inside the warp.
 template <bool WIDE>
-__global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np) {
+__global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
     typedef typename RecT<WIDE>::type Rec;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const ScanDev& s = scans[blockIdx.y];
     if ((s.wide != 0) != WIDE) return;
     const int n = s.counts[CNT_NPTS];
     const int w = threadIdx.x >> 5, lane = lane_id();
-    const int p = blockIdx.x * kNrmWarps + w;
+    int p = blockIdx.x * kNrmWarps + w;
+    if (mode == 1) {
+        if (p >= s.counts[CNT_NREDO]) return;
+        p = s.redo_list[p];
+    }
     if (p >= n) return;
     const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(s.recs);
     double qx, qy, qz;
@@ -452,6 +460,14 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
     syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
+    if (mode == 0) {
+        if (lane == 0) {
+            double* m = s.moments + 10 * (size_t)p;
+            m[0] = sx; m[1] = sy; m[2] = sz; m[3] = sxx; m[4] = sxy; m[5] = sxz; m[6] = syy; m[7] = syz; m[8] = szz; m[9] = (double)cnt;
+            s.nn_count[p] = cnt;
+        }
+        return;
+    }
     V3 nv{0.0, 0.0, 1.0};
     int redo = 0;
     if (lane == 0) {
@@ -531,6 +547,31 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     }
 }
 
+// One thread per point: covariance from the centred moment sums, analytic eigen-solve, normal.  Points whose two smallest
+// eigenvalues nearly coincide are appended to the scan's redo list for the canonical (oracle-order) re-summation.
+__global__ void __launch_bounds__(128) k_normals_eigen(const ScanDev* __restrict__ scans) {
+    const ScanDev& s = scans[blockIdx.y];
+    const int n = s.counts[CNT_NPTS];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double* m = s.moments + 10 * (size_t)p;
+    const int cnt = (int)m[9];
+    V3 nv;
+    double gap = 1.0;
+    if (cnt >= 3) {
+        // centred second moments: better conditioned than raw cumulants, equal to them up to rounding
+        const double inv = 1.0 / (double)cnt;
+        const double mx = m[0] * inv, my = m[1] * inv, mz = m[2] * inv;
+        nv = fast_eigen3x3(m[3] * inv - mx * mx, m[4] * inv - mx * my, m[5] * inv - mx * mz, m[6] * inv - my * my, m[7] * inv - my * mz,
+                           m[8] * inv - mz * mz, &gap);
+        if (gap < kIllGap && cnt <= kCanon) s.redo_list[atomicAdd(&s.counts[CNT_NREDO], 1)] = p;
+    } else {
+        nv = fast_eigen3x3(1, 0, 0, 1, 0, 1, &gap);   // Open3D: covariance = Identity when fewer than 3 neighbours
+    }
+    if (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) == 0.0) nv = {0.0, 0.0, 1.0};
+    reinterpret_cast<double4*>(s.normals)[p] = make_double4(nv.x, nv.y, nv.z, 0.0);
+}
+
 void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np_in, bool any_wide, bool any_narrow) {
     if (n_scans == 0 || cap_max == 0) return;
     NormalParams np = np_in;
@@ -548,8 +589,12 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
         cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem, d_scans, np);
-    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem, d_scans, np);
+    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem, d_scans, np, 0);
+    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem, d_scans, np, 0);
+    L.launch("normals_eigen", k_normals_eigen, dim3((cap_max + 127) / 128, n_scans), dim3(128), d_scans);
+    // ill-conditioned points (a few per cent): the grid is sized for the worst case, blocks past the list length exit
+    if (any_narrow) L.launch_smem("normals_redo", k_normals<false>, grid, block, smem, d_scans, np, 1);
+    if (any_wide) L.launch_smem("normals_redo", k_normals<true>, grid, block, smem, d_scans, np, 1);
 }
 
 }  // namespace arvc
