@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="keyframe pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=99, help="keyframe pairs per GPU per step (BASELINE.md config 2: the 99 pairs of a 100-scan sequence)")
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs of the cpu_baseline sample (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -47,7 +47,7 @@ def workload_config(pairs, n_gpus):
     return {"workload": "configs[1]: batched consecutive-keyframe point-to-plane ICP, 64-beam (OS1-64-like 64x1024) synthetic scans",
             "pairs_per_gpu_per_step": pairs, "scans_per_gpu_per_step": pairs + 1, "method": "icppointplane", "voxel_size": None,
             "max_corr_dist": 10.0, "criteria": "rel_fitness=1e-6 rel_rmse=1e-6 max_iter=30", "normals": "radius=0.3 max_nn=300",
-            "l2": "inputs larger than L2 (every step re-streams >250 MB of scans, grids and normals per GPU)",
+            "l2": "inputs larger than L2 (every step re-streams %d MB of scans, grids and normals per GPU)" % (12 * (pairs + 1)),
             "parallelism": "pairs sharded x%d, all-gather of 160 B records" % n_gpus}
 
 
@@ -183,7 +183,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs
-    seq = synth.Sequence(P + 1, synth.OS1_64, start=30.0 + 11.0 * rank)
+    seq = synth.Sequence(P + 1, synth.OS1_64, start=30.0 + 11.0 * rank, workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
     ids = np.arange(P + 1, dtype=np.int64)
     tg, sr = ids[:-1], ids[1:]
     init = np.array([seq.relative_odo(int(a), int(b)) for a, b in zip(tg, sr)])

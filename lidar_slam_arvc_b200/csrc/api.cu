@@ -315,7 +315,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     const double R = std::sqrt(p->max_radius2);
     const double pad = 0.5;
     const double ext = std::max(2 * (R + pad), p->max_height - p->min_height + 2 * pad);
-    double c0 = p->grid_cell > 0 ? p->grid_cell : 0.15;
+    double c0 = p->grid_cell > 0 ? p->grid_cell : (getenv("ARVC_GRID_CELL") ? atof(getenv("ARVC_GRID_CELL")) : 0.075);
     const double ncell_max = (double)((1 << kMortonBits) - 1);
     if (ext / c0 > ncell_max) c0 = ext / ncell_max;
     const double max_dist = p->grid_max_dist > 0 ? p->grid_max_dist : 10.0;
@@ -363,7 +363,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     for (Scan* s : todo) {
         const bool wide = s->f64 || voxel_on;
         unsigned tcap = 1024;
-        while (tcap < 4u * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;
+        while (tcap < (c0 < 0.12 ? 8u : 4u) * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;      // finer grids occupy more cells
         if (s->slab) { cudaFreeAsync(s->slab, ctx->L.stream); s->slab = nullptr; }
         SlabPlanner pp;
         plan_persistent(pp, *s, wide, voxel_on, tcap);

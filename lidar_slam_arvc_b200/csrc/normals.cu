@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     if (2 * total > kDenseFactor2 * np.max_nn && L > 0) {
         rtry = 1.1 * 3.0 * cl * sqrt((double)np.max_nn / (3.141592653589793 * (double)total));     // 10 % safety on the density model
         if (rtry < 0.95 * np.radius) {
-            const int Lf = L - 1;
-            const double cf = 0.5 * cl, rt = rtry * (1.0 + 1e-9) + 1e-12, rt2 = rtry * rtry;
+            int Lf = 0;                                   // finest level whose cells are at least half the trial radius
+            while (Lf < L - 1 && g.c0 * (double)(1 << Lf) < 0.5 * rtry) ++Lf;
+            const double cf = g.c0 * (double)(1 << Lf), rt = rtry * (1.0 + 1e-9) + 1e-12, rt2 = rtry * rtry;
             const int fx0 = cell_coord(qx - rt, g.ox, g.inv_c0) >> Lf, fx1 = cell_coord(qx + rt, g.ox, g.inv_c0) >> Lf;
             const int fy0 = cell_coord(qy - rt, g.oy, g.inv_c0) >> Lf, fy1 = cell_coord(qy + rt, g.oy, g.inv_c0) >> Lf;
             const int fz0 = cell_coord(qz - rt, g.oz, g.inv_c0) >> Lf, fz1 = cell_coord(qz + rt, g.oz, g.inv_c0) >> Lf;
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     double rq2 = r2;         // radius^2 the neighbourhood was finally searched with
     const uint2* runs = runs_full;
     int nruns = nfull;
+    if (np.debug & 2) { nfull = 0; ntry = 0; total = 0; }      // ablation: fixed per-point overhead only
     auto accumulate = [&](double x, double y, double z) {
         const double ux = x - qx, uy = y - qy, uz = z - qz;      // centred: exact differences of float32 payloads
         sx += ux; sy += uy; sz += uz;
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         break;
     }
 
-    if (np.debug && lane == 0 && (p % 997) == 0)      // ARVC_DEBUG_NORMALS=1: sampled per-point search statistics
+    if ((np.debug & 1) && lane == 0 && (p % 997) == 0)      // ARVC_DEBUG_NORMALS=1: sampled per-point search statistics
         printf("NRM p=%d total=%d ntry=%d total_try=%d rtry=%.3f used_trial=%d nruns=%d\n", p, total, ntry, total_try, rtry, (int)(runs == runs_try), nruns);
     cnt = warp_sum(cnt);
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
@@ -580,7 +582,7 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     np.r2_lo = (float)(np.r2 * (1.0 - 2e-6));
     np.r2_hi = (float)(np.r2 * (1.0 + 2e-6));
     np.bin_scale_f = (float)np.bin_scale;
-    np.debug = getenv("ARVC_DEBUG_NORMALS") ? 1 : 0;
+    np.debug = getenv("ARVC_DEBUG_NORMALS") ? atoi(getenv("ARVC_DEBUG_NORMALS")) : 0;
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
     const size_t smem = (size_t)kNrmWarps * kWarpSmem;
     static bool attr_set = false;

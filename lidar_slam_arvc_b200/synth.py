@@ -194,15 +194,27 @@ def noisy_odometry(poses, seed=4321, sigma_xy=0.02, sigma_yaw_deg=0.5):
     return out
 
 
-class Sequence:
-    """n_scans consecutive keyframes: scans (sensor frame, float32), GT poses, odometry poses."""
+def _scan_job(args):
+    world, sensor, T, seed = args
+    return scan_from_pose(world, sensor, T, seed)
 
-    def __init__(self, n_scans, sensor=OS1_64, world=None, seed_world=1234, seed_odo=4321, step=0.5, start=0.0):
+
+class Sequence:
+    """n_scans consecutive keyframes: scans (sensor frame, float32), GT poses, odometry poses.
+    `workers` > 1 ray-casts the scans in a process pool (same results, the per-scan seed fixes the noise)."""
+
+    def __init__(self, n_scans, sensor=OS1_64, world=None, seed_world=1234, seed_odo=4321, step=0.5, start=0.0, workers=1):
         self.world = world or World(seed_world)
         self.sensor = sensor
         self.poses = loop_trajectory(self.world, n_scans, step=step, start=start)
         self.odometry = noisy_odometry(self.poses, seed_odo)
-        self.scans = [scan_from_pose(self.world, sensor, T, 10000 + k) for k, T in enumerate(self.poses)]
+        jobs = [(self.world, sensor, T, 10000 + k) for k, T in enumerate(self.poses)]
+        if workers > 1 and n_scans > 2:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(min(workers, n_scans)) as pool:
+                self.scans = pool.map(_scan_job, jobs, chunksize=max(1, n_scans // (4 * workers)))
+        else:
+            self.scans = [_scan_job(j) for j in jobs]
 
     def relative_gt(self, i, j):
         return np.linalg.inv(self.poses[i]) @ self.poses[j]
