@@ -228,13 +228,16 @@ def main():
     # ---- value: scans resident in HBM, device time
     upload_all()
     barrier()
-    eng.profile_enable(True)
+    eng.profile_enable(not os.environ.get("ARVC_BENCH_NO_PROFILE"))
     l0 = eng.kernel_launches()
     tw0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    step_ms = []
     for _ in range(args.steps):
+        ts0 = time.perf_counter()
         rec_local = hot_path()
+        step_ms.append(round((time.perf_counter() - ts0) * 1e3, 1))
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -260,9 +263,12 @@ def main():
     # ---- e2e: host buffers -> result records on the host, every step
     barrier()
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(args.steps):
+        ts0 = time.perf_counter()
         upload_all()
         rec_all = hot_path()
+        e2e_step_ms.append(round((time.perf_counter() - ts0) * 1e3, 1))
     barrier()
     e2e_s = time.perf_counter() - t0
     time.sleep(0.25)
@@ -312,7 +318,7 @@ def main():
             "data": "synthetic", "config": workload_config(P, world), "ms_per_pair": dev_ms / (args.steps * P),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": float(t_s.item()) / args.steps * 1e3},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clk, "step_ms": step_ms, "e2e_step_ms": e2e_step_ms, "roofline": roofline,
             "mean_icp_updates": float(np.mean(own["updates"])), "icp_updates": [int(u) for u in own["updates"]], "points_per_scan": int(n_pts.mean())}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

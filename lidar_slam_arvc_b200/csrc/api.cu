@@ -39,6 +39,7 @@ struct Scan {
 struct PendingBatch {
     int n_pairs = 0;
     void* slab = nullptr;
+    size_t slab_bytes = 0;
     PairState* d_states = nullptr;
     PairState* h_states = nullptr;   // pinned, from the context's pool
     size_t h_bytes = 0;
@@ -83,6 +84,37 @@ struct arvc_ctx {
         return p;
     }
     void pinned_put(void* p, size_t bytes) { if (p) pinned_free.emplace_back(bytes, p); }
+
+    // Large transient device blocks (preprocessing scratch, per-batch ICP state) are recycled here instead of going
+    // back to the stream-ordered pool: a batch-sized block that the pool has split in the meantime would have to be
+    // re-created from the OS (hundreds of ms).  All use is on the context's single stream, so reuse is stream ordered.
+    std::vector<std::pair<size_t, void*>> dev_free;
+    void* dev_get(size_t bytes, size_t* got) {
+        int best = -1;
+        for (size_t i = 0; i < dev_free.size(); ++i)
+            if (dev_free[i].first >= bytes && (best < 0 || dev_free[i].first < dev_free[best].first)) best = (int)i;
+        if (best >= 0 && dev_free[best].first <= 2 * bytes + (1u << 20)) {
+            void* p = dev_free[best].second;
+            *got = dev_free[best].first;
+            dev_free.erase(dev_free.begin() + best);
+            return p;
+        }
+        const size_t cap = bytes + bytes / 8 + 256;      // head-room so that slightly larger batches still fit
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, cap, L.stream) != cudaSuccess) return nullptr;
+        *got = cap;
+        return p;
+    }
+    void dev_put(void* p, size_t bytes) {
+        if (!p) return;
+        dev_free.emplace_back(bytes, p);
+        while (dev_free.size() > 6) {                    // keep the cache small: drop the smallest block
+            size_t k = 0;
+            for (size_t i = 1; i < dev_free.size(); ++i) if (dev_free[i].first < dev_free[k].first) k = i;
+            cudaFreeAsync(dev_free[k].second, L.stream);
+            dev_free.erase(dev_free.begin() + k);
+        }
+    }
 
     int fail(int code, const std::string& msg) { error = msg; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -223,6 +255,7 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
 void arvc_ctx_destroy(arvc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto& df : ctx->dev_free) cudaFreeAsync(df.second, ctx->L.stream);
     for (auto& kv : ctx->pending) {
         if (kv.second.slab) cudaFreeAsync(kv.second.slab, ctx->L.stream);
         if (kv.second.h_states) cudaFreeHost(kv.second.h_states);
@@ -380,9 +413,10 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         cap_max = std::max(cap_max, s->n_raw);
         any_wide |= wide; any_narrow |= !wide;
     }
-    void* scratch = nullptr;
     const size_t scratch_bytes = scratch_plan.off + align_up(sizeof(ScanDev) * todo.size());
-    CK(cudaMallocAsync(&scratch, scratch_bytes, ctx->L.stream));
+    size_t scratch_cap = 0;
+    void* scratch = ctx->dev_get(scratch_bytes, &scratch_cap);
+    if (!scratch) return ctx->fail(ARVC_E_NOMEM, "scan_preprocess: device allocation failed");
     SlabPlanner sp;
     sp.base = reinterpret_cast<char*>(scratch);
     for (size_t i = 0; i < todo.size(); ++i) {
@@ -408,7 +442,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         s->voxel_on = voxel_on;
         s->params = *p;
     }
-    CK(cudaFreeAsync(scratch, ctx->L.stream));
+    ctx->dev_put(scratch, scratch_cap);
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     return ARVC_OK;
 }
@@ -577,7 +611,8 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
         }
         if (!pass) {
             plan = P;
-            CK(cudaMallocAsync(&pb.slab, plan.off, ctx->L.stream));
+            pb.slab = ctx->dev_get(plan.off, &pb.slab_bytes);
+            if (!pb.slab) return ctx->fail(ARVC_E_NOMEM, "icp: device allocation failed");
             if (trace) CK(cudaMemsetAsync(pb.slab, 0xff, plan.off, ctx->L.stream));   // untouched trace entries read as -1 / NaN
         } else {
             pb.d_states = d_states;
@@ -614,7 +649,7 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
 
 static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec) {
     CK(cudaStreamSynchronize(ctx->L.stream));
-    if (pb.slab) { cudaFreeAsync(pb.slab, ctx->L.stream); pb.slab = nullptr; }
+    if (pb.slab) { ctx->dev_put(pb.slab, pb.slab_bytes); pb.slab = nullptr; }
     struct Recycle { arvc_ctx* c; PendingBatch& b; ~Recycle() { c->pinned_put(b.h_states, b.h_bytes); b.h_states = nullptr; } } recycle{ctx, pb};
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     int err = 0;
@@ -651,7 +686,7 @@ int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, con
     if (!ctx || !ticket) return ARVC_E_ARG;
     PendingBatch pb;
     const int rc = icp_enqueue(ctx, n_pairs, tgt_ids, src_ids, init_T, p, false, pb, nullptr, nullptr, nullptr);
-    if (rc) { if (pb.slab) cudaFreeAsync(pb.slab, ctx->L.stream); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    if (rc) { ctx->dev_put(pb.slab, pb.slab_bytes); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
     *ticket = ctx->next_ticket++;
     ctx->pending[*ticket] = std::move(pb);
     return ARVC_OK;
@@ -693,7 +728,7 @@ int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* 
     double* d_st = nullptr;
     int cap = 0;
     int rc = icp_enqueue(ctx, 1, &tgt_id, &src_id, init_T, p, true, pb, &d_ct, &d_st, &cap);
-    if (rc) { if (pb.slab) cudaFreeAsync(pb.slab, ctx->L.stream); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    if (rc) { ctx->dev_put(pb.slab, pb.slab_bytes); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
     const int passes_max = p->max_iter + 1;
     std::vector<int> hct((size_t)cap * passes_max);
     std::vector<double> hst((size_t)passes_max * 18);
