@@ -138,6 +138,10 @@ int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* 
                    int32_t* corr, double* trace_T, double* trace_fitness, double* trace_rmse, int32_t* n_passes,
                    arvc_result_record* result);
 
+/* Load path helper (keyframe.py:41-45, o3d.io.read_point_cloud): LZF decompression of the payload of a
+ * `DATA binary_compressed` PCD file.  Host only.  Returns bytes written or -1 on a malformed stream. */
+long long arvc_lzf_decompress(const unsigned char* in, size_t n_in, unsigned char* out, size_t n_out);
+
 /* pinned host staging (optional; plain malloc'ed pointers work too, just slower for H2D) */
 void* arvc_host_alloc(size_t bytes);
 void arvc_host_free(void* p);

@@ -753,6 +753,31 @@ int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* 
     return ARVC_OK;
 }
 
+// LZF decompression (liblzf stream format) for DATA binary_compressed PCD files; host-only helper of the load path.
+// Returns the number of bytes written, or -1 on a malformed / oversized stream.
+long long arvc_lzf_decompress(const unsigned char* in, size_t n_in, unsigned char* out, size_t n_out) {
+    if ((!in && n_in) || (!out && n_out)) return -1;
+    size_t ip = 0, op = 0;
+    while (ip < n_in) {
+        const unsigned ctrl = in[ip++];
+        if (ctrl < 32) {                       // literal run of ctrl + 1 bytes
+            const size_t len = ctrl + 1;
+            if (ip + len > n_in || op + len > n_out) return -1;
+            std::memcpy(out + op, in + ip, len);
+            ip += len; op += len;
+        } else {                               // back reference
+            size_t len = ctrl >> 5;
+            if (len == 7) { if (ip >= n_in) return -1; len += in[ip++]; }
+            if (ip >= n_in) return -1;
+            const size_t off = ((size_t)(ctrl & 0x1f) << 8) + in[ip++] + 1;
+            len += 2;
+            if (off > op || op + len > n_out) return -1;
+            for (size_t k = 0; k < len; ++k) { out[op] = out[op - off]; ++op; }     // may overlap: byte by byte
+        }
+    }
+    return (long long)op;
+}
+
 void* arvc_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;

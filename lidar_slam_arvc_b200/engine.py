@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "arvc_kernel_launches", "arvc_scan_upload_f32", "arvc_scan_upload_f64", "arvc_scan_free", "arvc_scan_preprocess",
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
-    "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate",
+    "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
 ]
 
 
@@ -84,6 +84,8 @@ def load_library():
     lib.arvc_profile_enable.argtypes = [vp, c.c_int]
     lib.arvc_profile_report.argtypes = [vp, c.c_char_p, c.c_size_t]
     lib.arvc_scan_invalidate.argtypes = [vp, c.c_int64]
+    lib.arvc_lzf_decompress.argtypes = [c.c_char_p, c.c_size_t, vp, c.c_size_t]
+    lib.arvc_lzf_decompress.restype = c.c_longlong
     lib.arvc_host_alloc.argtypes = [c.c_size_t]
     lib.arvc_host_alloc.restype = vp
     lib.arvc_host_free.argtypes = [vp]
@@ -106,6 +108,16 @@ def _i64p(a):
 
 class EngineError(RuntimeError):
     pass
+
+
+def lzf_decompress(data, out_size):
+    """LZF-decompress `data` (bytes) into a new bytes object of exactly `out_size` bytes (host helper, no GPU needed)."""
+    lib = load_library()
+    out = ctypes.create_string_buffer(max(int(out_size), 1))
+    n = lib.arvc_lzf_decompress(bytes(data), len(data), ctypes.cast(out, ctypes.c_void_p), int(out_size))
+    if n != out_size:
+        raise ValueError("malformed LZF stream (got %d of %d bytes)" % (n, out_size))
+    return out.raw[:out_size]
 
 
 class Engine:

@@ -2,7 +2,7 @@
 
 Stands in for `o3d.io.read_point_cloud(filename)` at keyframemanager/keyframe.py:41-45 of the reference: the
 scan-matcher only needs the x/y/z fields.  Supports DATA ascii and DATA binary with float32 or float64
-coordinates; `binary_compressed` (LZF) is not implemented yet and raises.
+coordinates, and DATA binary_compressed (LZF, decompressed by the native library's host helper).
 Like Open3D's reader with default arguments, NaN/inf points are kept (the radius/height filter drops them).
 """
 import numpy as np
@@ -54,22 +54,50 @@ def read_pcd_xyz(filename):
             ftype = formats[names.index("x")]
             cols = [c.astype(ftype) for c in cols]
         elif data == "binary_compressed":
-            raise NotImplementedError("%s: DATA binary_compressed (LZF) is not supported yet" % filename)
+            # uint32 compressed size, uint32 uncompressed size, LZF stream; the payload is stored field by field (SoA)
+            import struct
+            from .engine import lzf_decompress
+            csize, usize = struct.unpack("<II", f.read(8))
+            raw = lzf_decompress(f.read(csize), usize)
+            cols, off = {}, 0
+            for nme, fmt in zip(names, formats):
+                dt = np.dtype(fmt)
+                if nme in ("x", "y", "z"):
+                    cols[nme] = np.frombuffer(raw, dtype=dt, count=n, offset=off)
+                off += dt.itemsize * n
+            cols = [cols["x"], cols["y"], cols["z"]]
         else:
             raise ValueError("%s: unknown DATA %s" % (filename, data))
     out_t = np.float32 if all(c.dtype == np.float32 for c in cols) else np.float64
     return np.ascontiguousarray(np.stack(cols, axis=1).astype(out_t, copy=False))
 
 
-def write_pcd_xyz(filename, xyz, binary=True):
-    """Write x y z as float32 (what LiDAR drivers produce), DATA binary or ascii."""
+def lzf_compress_literal(data):
+    """A valid LZF stream made of literal runs only (no back references): enough to write test fixtures."""
+    out = bytearray()
+    for i in range(0, len(data), 32):
+        chunk = data[i:i + 32]
+        out.append(len(chunk) - 1)
+        out += chunk
+    return bytes(out)
+
+
+def write_pcd_xyz(filename, xyz, binary=True, compressed=False):
+    """Write x y z as float32 (what LiDAR drivers produce), DATA binary, ascii or binary_compressed."""
     xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
     n = len(xyz)
+    kind = "binary_compressed" if compressed else ("binary" if binary else "ascii")
     header = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
-              "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n" % (n, n, "binary" if binary else "ascii"))
+              "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n" % (n, n, kind))
     with open(filename, "wb") as f:
         f.write(header.encode("ascii"))
-        if binary:
+        if compressed:
+            import struct
+            payload = np.ascontiguousarray(xyz.T).tobytes()          # field by field
+            comp = lzf_compress_literal(payload)
+            f.write(struct.pack("<II", len(comp), len(payload)))
+            f.write(comp)
+        elif binary:
             f.write(xyz.tobytes())
         else:
             for p in xyz:

@@ -37,6 +37,15 @@ def test_pcd_roundtrip(tmp_path):
     back = pcd.read_pcd_xyz(fn)
     assert back.dtype == np.float64
     np.testing.assert_array_equal(back[:, 1], np.arange(5) * 2.0)
+    # binary_compressed (LZF): literal-only stream written by the test helper, and a hand-made stream with back references
+    fn = str(tmp_path / "c.pcd")
+    pcd.write_pcd_xyz(fn, xyz, compressed=True)
+    np.testing.assert_array_equal(pcd.read_pcd_xyz(fn), xyz)
+    from lidar_slam_arvc_b200.engine import lzf_decompress
+    stream = bytes([2]) + b"abc" + bytes([(4 << 5) | 0, 2]) + bytes([0]) + b"Z" + bytes([(7 << 5) | 0, 3, 0])
+    assert lzf_decompress(stream, 3 + 6 + 1 + 12) == b"abcabcabcZ" + b"Z" * 12
+    with pytest.raises(ValueError):
+        lzf_decompress(bytes([(1 << 5) | 0, 9]), 3)            # back reference before the start of the output
     empty = str(tmp_path / "e.pcd")
     pcd.write_pcd_xyz(empty, np.zeros((0, 3)))
     assert pcd.read_pcd_xyz(empty).shape == (0, 3)
