@@ -305,7 +305,10 @@ def main():
             traffic = tj["normals"]["dram_bytes_per_scan"] * len(ids)
         elif name == "icp_pass" and "icp_pass" in tj:
             traffic = tj["icp_pass"]["dram_bytes_per_pair_pass"] * float(sum(int(x) for x in own["passes"])) * args.steps / n_launch
-    roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    ncu_util = None
+    if os.path.exists(tpath):
+        ncu_util = {k: v for k, v in json.load(open(tpath)).get(name, {}).items() if k.endswith("_pct")}
+    roofline = {"bound": "hbm", "kernel": name, "ncu_utilisation_pct": ncu_util, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launches": n_launch, "kernel_ms_total": tot_ms,
                 "kernel_share_of_device_time": tot_ms / dev_ms if dev_ms > 0 else None,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),

@@ -53,8 +53,10 @@ __host__ __device__ __forceinline__ unsigned long long cell_key(int level, unsig
     return ((unsigned long long)(level + 1) << 32) | (unsigned long long)prefix;
 }
 __host__ __device__ __forceinline__ unsigned hash_key(unsigned long long k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-    return (unsigned)k;
+    // 32-bit mix of (Morton prefix, level): a handful of integer instructions instead of a 64-bit murmur finaliser
+    unsigned h = (unsigned)k * 0x9E3779B1u ^ ((unsigned)(k >> 32) * 0x85EBCA6Bu);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
 }
 
 __host__ __device__ __forceinline__ unsigned spread3(unsigned v) {   // 10 bits -> every third bit

@@ -292,11 +292,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         const int tot = trial ? total_try : total;
         const double bin_scale = trial ? (double)kBins / rq2 : np.bin_scale;
         const float bin_scale_f = (float)bin_scale;
-        const float rq2_lo = trial ? (float)(rq2 * (1.0 - 2e-6)) : np.r2_lo, rq2_hi = trial ? (float)(rq2 * (1.0 + 2e-6)) : np.r2_hi;
+        float rq2_lo = trial ? (float)(rq2 * (1.0 - 2e-6)) : np.r2_lo, rq2_hi = trial ? (float)(rq2 * (1.0 + 2e-6)) : np.r2_hi;
+        float bsf = bin_scale_f;
+        // pin the loop-invariant screening constants in registers (the compiler otherwise re-derives them from the
+        // float64 radius inside the candidate loops: two DMUL + two F2F per iteration)
+        asm volatile("" : "+f"(rq2_lo), "+f"(rq2_hi), "+f"(bsf));
         // d2 -> bucket, monotone in the exact d2; the float32 shortcut is taken only when it cannot cross a bucket edge
         auto bucket = [&](const CandEval<WIDE>& c, double& d2, bool& have) -> int {
             if constexpr (!WIDE) {
-                const float u = c.d2f * bin_scale_f;
+                const float u = c.d2f * bsf;
                 const int b = (int)u;
                 const float fr = u - (float)b;
                 if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) return b;
