@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs of the cpu_baseline sample (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-voxel", action="store_true", help="skip the extra voxel_size 0.2 measurement")
     return ap.parse_args()
 
 
@@ -323,6 +324,21 @@ def main():
                     "ms_per_step": float(t_s.item()) / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clk, "step_ms": step_ms, "e2e_step_ms": e2e_step_ms, "roofline": roofline,
             "mean_icp_updates": float(np.mean(own["updates"])), "icp_updates": [int(u) for u in own["updates"]], "points_per_scan": int(n_pts.mean())}
+
+    # ---- extra (BASELINE.md config 2 is reported for voxel_size None and 0.2): same batch with voxel down-sampling on
+    if world == 1 and not args.no_voxel:
+        ppv = eng.make_preprocess_params(voxel_size=0.2)
+        for _ in range(2):
+            eng.invalidate(ids); eng.preprocess(ids, ppv); rv = eng.icp_batch(tg, sr, init, ip)
+        eng.sync()
+        tv0 = time.perf_counter()
+        nv = max(2, args.steps // 3)
+        for _ in range(nv):
+            eng.invalidate(ids); eng.preprocess(ids, ppv); rv = eng.icp_batch(tg, sr, init, ip)
+        tv = time.perf_counter() - tv0
+        line["voxel_0p2"] = {"value": P * nv / tv, "unit": UNIT, "steps": nv, "points_per_scan": int(np.mean([eng.info(int(k))["n_points"] for k in ids[:8]])),
+                             "mean_icp_updates": float(np.mean(rv["updates"])), "note": "same pairs, voxel_size 0.2 (float64 records path), wall clock"}
+        eng.invalidate(ids)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
