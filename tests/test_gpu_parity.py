@@ -339,3 +339,26 @@ def test_loop_closure_batch_properties(eng):
     np.testing.assert_array_equal(merged["rmse"], res["rmse"])
     for k in range(len(seq.scans)):
         eng.free(100 + k)
+
+
+@pytest.mark.parametrize("src_f64,tgt_f64", [(True, False), (False, True)])
+def test_icp_mixed_record_types(eng, seq16, src_f64, tgt_f64):
+    """Source and target stored with different record widths (float64 upload vs float32 PCD payload)."""
+    eng.upload(40, seq16.scans[0].astype(np.float64) if tgt_f64 else seq16.scans[0])
+    eng.upload(41, seq16.scans[1].astype(np.float64) if src_f64 else seq16.scans[1])
+    eng.preprocess([40, 41], eng.make_preprocess_params())
+    init = seq16.relative_odo(0, 1)
+    for method in (engine.P2PLANE, engine.P2P):
+        tr = eng.icp_trace(40, 41, init, eng.make_icp_params(method))
+        tgt, tn = eng.get_points(40, normals=True)
+        src = eng.get_points(41)
+        for k in (0, tr["passes"] - 1):
+            corr, _, fit, _ = orc.correspondences(src, tgt, tr["T"][k], 10.0)
+            np.testing.assert_array_equal(tr["corr"][k], corr)
+        ref = orc.icp(src, tgt, orc.estimate_normals(tgt) if method == engine.P2PLANE else None, init,
+                      orc.P2PLANE if method == engine.P2PLANE else orc.P2P)
+        assert tr["result"]["passes"] == ref.passes
+        assert_transform_close(tr["result"]["T"], ref.transformation)
+        assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
+    eng.free(40)
+    eng.free(41)
