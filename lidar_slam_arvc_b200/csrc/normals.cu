@@ -121,7 +121,7 @@ constexpr int kScratch = kCanon * 20;  // bytes of the two overlapping layouts a
 constexpr int kTryRuns = 160;          // cells of the trial ball (6^3 = 216 before box pruning)
 constexpr int kWarpSmem = kScratch + (64 + kTryRuns) * 8;   // + cell runs, which outlive both layouts
 constexpr int kDenseFactor2 = 3;       // neighbourhoods with more than kDenseFactor2/2 * max_nn candidates try a smaller radius first
-static_assert(kBins * 4 + kCand * 16 <= kScratch, "selection layout must fit");
+static_assert(kBins * 4 + kCand * 16 + 16 <= kScratch, "selection layout must fit");
 constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
 
 __device__ __forceinline__ bool key_less(double d2a, int ia, double d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
@@ -325,9 +325,21 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
                 for (unsigned j = run.x + lane; j < run.y; j += 32) {
                     CandEval<WIDE> c;
                     c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                    double d2 = 0;
-                    bool have = false;
-                    if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
+                    if constexpr (!WIDE) {
+                        // float32 bucket coordinate: beyond the last bucket -> outside the radius; safely inside a bucket
+                        // -> count it; within 2e-3 of an edge (or in the last bucket) -> decide exactly
+                        const float u = c.d2f * bsf;
+                        if (u > (float)kBins + 2e-3f) continue;
+                        const int b = (int)u;
+                        const float fr = u - (float)b;
+                        if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) { atomicAdd(&hist[b], 1); continue; }
+                        const double d2 = c.exact(qx, qy, qz);
+                        if (d2 < rq2) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
+                    } else {
+                        double d2 = 0;
+                        bool have = false;
+                        if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
+                    }
                 }
             }
             __syncwarp();
@@ -363,29 +375,62 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
 
         // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
         int ncand = 0;
-        for (int rr = 0; rr < nruns; ++rr) {
-            const uint2 run = runs[rr];
-            for (unsigned t = run.x; t < run.y; t += 32) {
-                const unsigned j = t + lane;
-                bool hit = false;
-                double d2 = 0;
-                CandEval<WIDE> c;
-                if (j < run.y) {
+        if constexpr (!WIDE) {
+            // float32 bucket coordinate u = d2f * buckets / r^2 (absolute error < 1e-3): two compares settle almost every
+            // candidate - certainly below bucket bstar (taken), certainly above it (dropped); the rest is decided exactly
+            int* ncand_s = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 16);
+            if (lane == 0) *ncand_s = 0;
+            __syncwarp();
+            const float u_lo = (float)min(bstar, kBins) - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bstar + 1) + 2e-3f;
+            for (int rr = 0; rr < nruns; ++rr) {
+                const uint2 run = runs[rr];
+                for (unsigned j = run.x + lane; j < run.y; j += 32) {
+                    CandEval<WIDE> c;
                     c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                    bool have = false;
-                    if (in_radius(c, d2, have)) {
-                        const int b = bstar == kBins ? 0 : bucket(c, d2, have);
-                        if (b < bstar) accumulate(c.x(), c.y(), c.z());
-                        else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
+                    const float u = c.d2f * bsf;
+                    if (u < u_lo) {
+                        accumulate(c.x(), c.y(), c.z());
+                    } else if (u <= u_hi) {
+                        const double d2 = c.exact(qx, qy, qz);
+                        if (d2 < rq2) {
+                            const int b = min(kBins - 1, (int)(d2 * bin_scale));
+                            if (b < bstar) {
+                                accumulate(c.x(), c.y(), c.z());
+                            } else if (b == bstar) {
+                                const int slot = atomicAdd(ncand_s, 1);
+                                if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                            }
+                        }
                     }
                 }
-                if (bstar != kBins) {
-                    const unsigned m = __ballot_sync(kFull, hit);
-                    if (hit) {
-                        const int slot = ncand + __popc(m & ((1u << lane) - 1u));
-                        if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+            }
+            __syncwarp();
+            ncand = *ncand_s;
+        } else {
+            for (int rr = 0; rr < nruns; ++rr) {
+                const uint2 run = runs[rr];
+                for (unsigned t = run.x; t < run.y; t += 32) {
+                    const unsigned j = t + lane;
+                    bool hit = false;
+                    double d2 = 0;
+                    CandEval<WIDE> c;
+                    if (j < run.y) {
+                        c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                        bool have = false;
+                        if (in_radius(c, d2, have)) {
+                            const int b = bstar == kBins ? 0 : bucket(c, d2, have);
+                            if (b < bstar) accumulate(c.x(), c.y(), c.z());
+                            else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
+                        }
                     }
-                    ncand += __popc(m);
+                    if (bstar != kBins) {
+                        const unsigned m = __ballot_sync(kFull, hit);
+                        if (hit) {
+                            const int slot = ncand + __popc(m & ((1u << lane) - 1u));
+                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                        }
+                        ncand += __popc(m);
+                    }
                 }
             }
         }
