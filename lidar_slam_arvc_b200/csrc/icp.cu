@@ -352,8 +352,10 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
     PairState* st = pr.state;
     if (st->done) return;
     const int n = src.counts[CNT_NPTS];
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_cnt[8], s_base;
+#pragma unroll 1
+    for (int chunk = blockIdx.x; chunk * 256 < n; chunk += gridDim.x) {
+    const int i = chunk * 256 + threadIdx.x;
     bool need = false;
     if (i < n) {
         double px, py, pz;
@@ -385,7 +387,6 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
     }
     // block-ordered append, padded to a multiple of kG with -1: the kG entries a search group serves then always come
     // from one block of 256 consecutive (Morton-sorted) source points, which keeps the groups spatially compact
-    __shared__ int s_cnt[8], s_base;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(kFull, need);
     if (lane == 0) s_cnt[w] = __popc(m);
@@ -398,6 +399,8 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
     __syncthreads();
     if (need) pr.list[s_base + before + __popc(m & ((1u << lane) - 1u))] = i;
     if ((int)threadIdx.x < padded - total) pr.list[s_base + total + threadIdx.x] = -1;
+    __syncthreads();
+    }   // chunk loop
 }
 
 template <bool SW, bool TW>
@@ -416,15 +419,17 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
     const int n = pass == 0 ? src.counts[CNT_NPTS] : st->nlist;       // pass 0 searches every point
-    if ((int)(blockIdx.x * kIcpBlock) >= n) return;
-    const long long t_begin = clock64();
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
     const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
-    double T[12];
+    // late passes run on a reduced grid (a finished pair then costs few block launches): each block strides over
+    // the chunks of kIcpBlock work-list entries; the warps of a block share nothing, so no block barrier is needed
+#pragma unroll 1
+    for (int chunk = blockIdx.x; chunk * kIcpBlock < n; chunk += gridDim.x) {
+    const long long t_begin = clock64();
+    const int t_idx = chunk * kIcpBlock + threadIdx.x;
+    double T[12];                        // re-read per chunk: keeping it live across the loop costs 24 registers
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->T[k];
-
-    const int t_idx = blockIdx.x * kIcpBlock + threadIdx.x;
     const int i = t_idx < n ? (pass == 0 ? t_idx : pr.list[t_idx]) : -1;      // -1: padding entry
     // ---- per lane: transform the source point, bound the search with the previous pass' match
     double sx = 0, sy = 0, sz = 0;
@@ -692,14 +697,19 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
         while (bkt < 6 && dt > (20000ll << bkt)) ++bkt;      // 20k cycles ~ 10 us, doubling
         atomicAdd(&pr.state->dbg[1 + bkt], 1ull);
         atomicMax(&pr.state->dbg[0], (unsigned long long)dt);
-        if (dt > 400000) printf("SLOW warp pass=%d pair=%d blk=%d total=%.0fus union=%.0fus fallback=%.0fus\n", pass, (int)blockIdx.y, (int)blockIdx.x, dt / 1965.0, (t_union_end - t_begin) / 1965.0, (clock64() - t_union_end) / 1965.0);
+        if (dt > 400000) printf("SLOW warp pass=%d pair=%d blk=%d total=%.0fus union=%.0fus fallback=%.0fus\n", pass, (int)blockIdx.y, chunk, dt / 1965.0, (t_union_end - t_begin) / 1965.0, (clock64() - t_union_end) / 1965.0);
     }
     if (ip.debug & 1) {
         const int u = warp_sum(stat_union), f = warp_sum(stat_fb), ac = warp_sum(i >= 0 ? 1 : 0);
         if (lane == 0) { atomicAdd(&pr.state->dbg[0], (unsigned long long)ac); atomicAdd(&pr.state->dbg[1], (unsigned long long)u);
                          atomicAdd(&pr.state->dbg[2], (unsigned long long)f); }
     }
+    __syncwarp();
+    }   // chunk loop
 }
+
+constexpr int kAccPts = 4;                                  // source points per lane of the accumulation kernel
+constexpr int kAccBlockPts = kIcpBlock * kAccPts;
 
 template <int METHOD, bool SW, bool TW>
 __global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
@@ -712,59 +722,62 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restri
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
     const int n = src.counts[CNT_NPTS];
-    const int nblk = max(1, (n + kIcpBlock - 1) / kIcpBlock);
-    if ((int)blockIdx.x >= nblk) return;
+    const int nblk = max(1, (n + kAccBlockPts - 1) / kAccBlockPts);
     const int lane = lane_id();
-    const int i = blockIdx.x * kIcpBlock + threadIdx.x;
+#pragma unroll 1
+    for (int chunk = blockIdx.x; chunk < nblk; chunk += gridDim.x) {
+    const int base = chunk * kAccBlockPts + (threadIdx.x >> 5) * (32 * kAccPts) + lane;
     double acc[kNS];
 #pragma unroll
     for (int k = 0; k < kNS; ++k) acc[k] = 0.0;
-    if (i < n) {
+    const double* T = st->T;
+    const double T0 = T[0], T1 = T[1], T2 = T[2], T3 = T[3], T4 = T[4], T5 = T[5], T6 = T[6], T7 = T[7], T8 = T[8], T9 = T[9],
+                 T10 = T[10], T11 = T[11];
+#pragma unroll 1
+    for (int j = 0; j < kAccPts; ++j) {
+        const int i = base + j * 32;
+        if (i >= n) break;
         const int pos = pr.prev[i];
         int sidx = 0;
-        if (pos >= 0 || pr.corr_trace) {
-            double px, py, pz;
-            load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
-            if (pos >= 0) {
-                const double* T = st->T;
-                const double sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
-                const double sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-                const double sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-                double tx, ty, tz;
-                int tidx;
-                load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pos, tx, ty, tz, tidx);
-                acc[27] = sqdist(sx, sy, sz, tx, ty, tz);
-                acc[28] = 1.0;
-                if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = tidx;
-                if (METHOD == 1) {
-                    const double4 nv = reinterpret_cast<const double4*>(tgt.normals)[pos];
-                    const double r = (sx - tx) * nv.x + (sy - ty) * nv.y + (sz - tz) * nv.z;
-                    const double J[6] = {sy * nv.z - sz * nv.y, sz * nv.x - sx * nv.z, sx * nv.y - sy * nv.x, nv.x, nv.y, nv.z};
-                    int t = 0;
+        if (pos < 0 && !pr.corr_trace) continue;
+        double px, py, pz;
+        load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
+        if (pos < 0) { pr.corr_trace[(size_t)pass * src.cap + sidx] = -1; continue; }
+        const double sx = T0 * px + T1 * py + T2 * pz + T3;
+        const double sy = T4 * px + T5 * py + T6 * pz + T7;
+        const double sz = T8 * px + T9 * py + T10 * pz + T11;
+        double tx, ty, tz;
+        int tidx;
+        load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pos, tx, ty, tz, tidx);
+        acc[27] += sqdist(sx, sy, sz, tx, ty, tz);
+        acc[28] += 1.0;
+        if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = tidx;
+        if (METHOD == 1) {
+            const double4 nv = reinterpret_cast<const double4*>(tgt.normals)[pos];
+            const double r = (sx - tx) * nv.x + (sy - ty) * nv.y + (sz - tz) * nv.z;
+            const double J[6] = {sy * nv.z - sz * nv.y, sz * nv.x - sx * nv.z, sx * nv.y - sy * nv.x, nv.x, nv.y, nv.z};
+            int t = 0;
 #pragma unroll
-                    for (int a = 0; a < 6; ++a)
+            for (int a = 0; a < 6; ++a)
 #pragma unroll
-                        for (int c = a; c < 6; ++c) acc[t++] = J[a] * J[c];
+                for (int c = a; c < 6; ++c) acc[t++] += J[a] * J[c];
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) acc[21 + a] = J[a] * r;
-                } else {
-                    acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
-                    acc[6] = tx * sx; acc[7] = tx * sy; acc[8] = tx * sz;
-                    acc[9] = ty * sx; acc[10] = ty * sy; acc[11] = ty * sz;
-                    acc[12] = tz * sx; acc[13] = tz * sy; acc[14] = tz * sz;
-                }
-            } else {
-                pr.corr_trace[(size_t)pass * src.cap + sidx] = -1;
-            }
+            for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+        } else {
+            acc[0] += sx; acc[1] += sy; acc[2] += sz; acc[3] += tx; acc[4] += ty; acc[5] += tz;
+            acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
+            acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
+            acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
         }
     }
-    double* row = pr.partials + ((size_t)blockIdx.x * (kIcpBlock / 32) + (threadIdx.x >> 5)) * kSumStride;
+    double* row = pr.partials + ((size_t)chunk * (kIcpBlock / 32) + (threadIdx.x >> 5)) * kSumStride;
 #pragma unroll
     for (int k = 0; k < kNS; ++k) {
         if (METHOD == 0 && k >= 15 && k < 27) continue;
         const double v = warp_sum(acc[k]);
         if (lane == 0) row[k] = v;
     }
+    }   // chunk loop
 }
 
 // Finish kernel, one block per pair: fixed-order reduction of the warps' partial sums, solve, cumulative
@@ -779,7 +792,7 @@ __global__ void __launch_bounds__(256) k_icp_finish(const PairDev* __restrict__ 
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     const int n = src.counts[CNT_NPTS];
-    const int nrows = max(1, (n + kIcpBlock - 1) / kIcpBlock) * (kIcpBlock / 32);
+    const int nrows = max(1, (n + kAccBlockPts - 1) / kAccBlockPts) * (kIcpBlock / 32);
     const int lane = lane_id(), w = threadIdx.x >> 5;
     double v = 0;
     for (int r = w; r < nrows; r += 8) v += pr.partials[(size_t)r * kSumStride + lane];
@@ -837,7 +850,11 @@ static const char* pass_name(int pass) {   // "icp_pass_00" ... so that the prof
 template <int METHOD>
 static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, int cap_max, const IcpParams& ip, int pass, int combos_mask) {
     const char* nm = pass_name(pass);
-    const dim3 g256((cap_max + 255) / 256, grid.y);
+    // Pairs converge after ~5-12 passes but max_iter + 1 are enqueued (no host round trip): the later the pass, the
+    // smaller the grid, so that the blocks of finished pairs cost next to nothing; the kernels stride over their chunks.
+    const int sh_pts = pass < 4 ? 0 : (pass < 10 ? 2 : 3), sh_search = pass < 3 ? 0 : (pass < 5 ? 1 : 2);
+    const dim3 g256(max(1, ((cap_max + 255) / 256) >> sh_pts), grid.y);
+    grid.x = max(1u, grid.x >> sh_search);
     if (pass > 0) {
         if (combos_mask & 1) L.launch("icp_select", k_icp_select<false, false>, g256, dim3(256), d_pairs, ip, pass);
         if (combos_mask & 2) L.launch("icp_select", k_icp_select<false, true>, g256, dim3(256), d_pairs, ip, pass);
@@ -848,10 +865,11 @@ static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, int ca
     if (combos_mask & 2) L.launch(nm, k_icp_search<false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
     if (combos_mask & 4) L.launch(nm, k_icp_search<true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
     if (combos_mask & 8) L.launch(nm, k_icp_search<true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 1) L.launch("icp_accum", k_icp_accum<METHOD, false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch("icp_accum", k_icp_accum<METHOD, false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch("icp_accum", k_icp_accum<METHOD, true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch("icp_accum", k_icp_accum<METHOD, true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
+    const dim3 gacc(max(1, ((cap_max + kAccBlockPts - 1) / kAccBlockPts) >> sh_pts), grid.y);
+    if (combos_mask & 1) L.launch("icp_accum", k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 2) L.launch("icp_accum", k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 4) L.launch("icp_accum", k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
+    if (combos_mask & 8) L.launch("icp_accum", k_icp_accum<METHOD, true, true>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
     L.launch("icp_finish", k_icp_finish<METHOD>, dim3(grid.y), dim3(256), d_pairs, ip, pass);
 }
 
