@@ -30,14 +30,36 @@ def rot2quaternion(R):
     return np.hstack((s, np.sqrt(max(0.0, 1 - s ** 2)) / nm * k))
 
 
-def rot2euler_zyx(R):
-    """(alpha, beta, gamma) with R = Rx(alpha) Ry(beta) Rz(gamma) convention is the reference's; here the common
-    XYZ-fixed decomposition R = Rz(g) Ry(b) Rx(a) is returned as [a, b, g] for diagnostics only."""
+def _wrap(angles):
+    return np.arctan2(np.sin(angles), np.cos(angles))
+
+
+def rot2euler(R):
+    """Both solutions (alpha, beta, gamma) of R = Rx(alpha) Ry(beta) Rz(gamma) (XYZ, mobile axes), wrapped to
+    [-pi, pi] - the convention of the reference's artelib/tools.py:241-275 (pinned by tests/golden/se3_helpers.npz).
+    sin(beta) = R[0, 2]; within 1e-4 of gimbal lock alpha is fixed to 0 / pi."""
     R = np.asarray(R, dtype=np.float64)
-    b = -np.arcsin(np.clip(R[2, 0], -1, 1))
-    a = np.arctan2(R[2, 1], R[2, 2])
-    g = np.arctan2(R[1, 0], R[0, 0])
-    return np.array([a, b, g])
+    s = float(np.clip(R[0, 2], -1.0, 1.0))
+    b1 = np.arcsin(s)
+    if abs(abs(R[0, 2]) - 1.0) > 1e-4:
+        sols = []
+        for b in (b1, np.pi - b1):
+            c = np.sign(np.cos(b))
+            sols.append([np.arctan2(-c * R[1, 2], c * R[2, 2]), b, np.arctan2(-c * R[0, 1], c * R[0, 0])])
+    else:
+        sg = 1.0 if b1 > 0 else -1.0
+        g = np.arctan2(sg * R[1, 0], R[1, 1])
+        sols = [[0.0, b1, g], [np.pi, sg * np.pi / 2, g - np.pi]]
+    return _wrap(np.array(sols[0])), _wrap(np.array(sols[1]))
+
+
+class Euler:
+    """Minimal stand-in of artelib.euler.Euler: the angles live in `.abg`."""
+    def __init__(self, abg):
+        self.abg = np.asarray(abg.abg if isinstance(abg, Euler) else abg, dtype=np.float64)
+
+    def __str__(self):
+        return str(self.abg)
 
 
 class HomogeneousMatrix:
@@ -72,7 +94,8 @@ class HomogeneousMatrix:
         return self.array[0:3, 3]
 
     def euler(self):
-        return rot2euler_zyx(self.array)
+        e1, e2 = rot2euler(self.array)
+        return Euler(e1), Euler(e2)
 
     def __mul__(self, other):
         if isinstance(other, HomogeneousMatrix) or hasattr(other, "array"):
@@ -91,7 +114,7 @@ class HomogeneousMatrix:
     def t2v(self, n=2):
         if n == 2:
             return np.array([self.array[0, 3], self.array[1, 3], np.arctan2(self.array[1, 0], self.array[0, 0])])
-        e = rot2euler_zyx(self.array)
+        e = rot2euler(self.array)[0]
         return np.array([self.array[0, 3], self.array[1, 3], self.array[2, 3], e[0], e[1], e[2]])
 
 

@@ -76,7 +76,7 @@ def main():
                         defaults=np.array([kf.min_radius, kf.max_radius, kf.min_height, kf.max_height], dtype=np.float64))
 
     # SE(3) helper goldens
-    mats, invs, prods, quats, eulers = [], [], [], [], []
+    mats, invs, prods, quats, eulers, eulers2 = [], [], [], [], [], []
     for _ in range(32):
         e = rng.uniform(-np.pi, np.pi, 3)
         e[1] = rng.uniform(-1.4, 1.4)
@@ -90,8 +90,17 @@ def main():
         prods.append((H * H.inv() * H).array)
         quats.append(np.array(tools.rot2quaternion(T)))
         eulers.append(np.array(tools.rot2euler(T)[0]))
+        eulers2.append(np.array(tools.rot2euler(T.copy())[1]))
+    gimbal_mats, gimbal_e1, gimbal_e2 = [], [], []
+    for k in range(8):                                   # beta = +-pi/2: the degenerate branch of rot2euler
+        e = rng.uniform(-np.pi, np.pi, 3)
+        e[1] = np.pi / 2 * (1 if k % 2 == 0 else -1)
+        R = np.array(tools.euler2rot(e))[:3, :3]
+        e1, e2 = tools.rot2euler(R.copy())
+        gimbal_mats.append(R); gimbal_e1.append(np.array(e1)); gimbal_e2.append(np.array(e2))
     np.savez_compressed(os.path.join(OUT, "se3_helpers.npz"), mats=np.array(mats), invs=np.array(invs),
-                        prods=np.array(prods), quats=np.array(quats), eulers=np.array(eulers))
+                        prods=np.array(prods), quats=np.array(quats), eulers=np.array(eulers), eulers2=np.array(eulers2),
+                        gimbal_mats=np.array(gimbal_mats), gimbal_e1=np.array(gimbal_e1), gimbal_e2=np.array(gimbal_e2))
     print("wrote", os.listdir(OUT))
 
 

@@ -80,3 +80,56 @@ def test_batched_loop_closing_equals_sequential(kfm_module, tmp_path):
     km.method = "fpfh"
     with pytest.raises(NotImplementedError):
         km.pre_process(0)
+
+
+def test_loop_closing_triangle_one_device_batch(kfm_module, tmp_path):
+    """SURVEY.md §8 f-1 on the GPU: the batched LoopClosing adds exactly the edges of the pair-by-pair call sequence of
+    the reference (loopclosing.py:154-184, restated by the drop-in's sequential path), bit for bit, and its
+    registrations agree with the oracle."""
+    from test_loopclosing_cpu import FakeGraphSLAM, noisy_estimate, small_loop_sequence
+    for m in [k for k in sys.modules if k.split(".")[0] == "graphslam"]:
+        del sys.modules[m]
+    import graphslam.loopclosing as lc_mod
+    assert lc_mod.__file__.startswith(DROPIN)
+    seq = small_loop_sequence()
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq)
+    km = kfm_module.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icppointplane")
+    km.add_keyframes(keyframe_sampling=1)
+    T0_gps = HomogeneousMatrix(synth.pose_matrix(0.36, 0.0, 0.0, 0.0))
+    est = noisy_estimate(seq)
+    last = len(seq.poses) - 1
+
+    class Sequential:                      # the reference manager's surface only -> pair-by-pair path
+        def __init__(self, km):
+            self.km, self.n_icp = km, 0
+
+        def load_pointcloud(self, i):
+            self.km.load_pointcloud(i)
+
+        def pre_process(self, i):
+            self.km.pre_process(i)
+
+        def compute_transformation(self, i, j, Tij):
+            self.n_icp += 1
+            return self.km.compute_transformation(i, j, Tij)
+
+    g_seq, g_bat = FakeGraphSLAM(est, T0_gps), FakeGraphSLAM(est, T0_gps)
+    sq = Sequential(km)
+    np.random.seed(11)
+    a_seq = lc_mod.LoopClosing(g_seq).loop_closing_triangle(current_index=last, number_of_triplets_loop_closing=4, keyframe_manager=sq)
+    np.random.seed(11)
+    a_bat = lc_mod.LoopClosing(g_bat).loop_closing_triangle(current_index=last, number_of_triplets_loop_closing=4, keyframe_manager=km)
+    assert sq.n_icp == 8 and a_seq == a_bat and len(a_bat) > 0
+    assert len(g_seq.edges) == len(g_bat.edges) == len(a_bat)
+    pre = {}
+    for (i, j, T, _), (i2, j2, T2, _) in zip(g_seq.edges, g_bat.edges):
+        assert (i, j) == (i2, j2)
+        np.testing.assert_array_equal(T, T2)
+        for k in (i, j):
+            if k not in pre:
+                pre[k] = orc.preprocess(seq.scans[k])
+        init = np.linalg.inv(est[i]) @ est[j]
+        ref = orc.icp(pre[j][0], pre[i][0], pre[i][1], init, orc.P2PLANE)
+        want = np.linalg.inv(T0_gps.array) @ ref.transformation @ T0_gps.array
+        assert np.abs(T2 - want).max() < 1e-4
