@@ -91,6 +91,15 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
 int arvc_scan_info(arvc_ctx* ctx, int64_t scan_id, int* n_raw, int* n_filtered, int* n_points, int* has_normals);
 /* np.asarray(pointcloud_filtered.points / .normals): xyz[n_points*3], normals[n_points*3] (NULL to skip), cloud order. */
 int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* normals);
+/* KeyFrameManager.build_map (keyframemanager.py:154-184) without the GUI, for a batch of uploaded keyframes: per
+ * keyframe filter_radius_height(radii, heights) (keyframe.py:74-94) -> down_sample (:108-111) ->
+ * KeyFrame.transform(T_i) (:399-400, Open3D PointCloud::Transform incl. the division by w) -> concatenation in
+ * keyframe order.  `p` carries the map's radii / heights / voxel size (want_normals = 0).  T: n_scans row-major 4x4.
+ * xyz_out[capacity_points*3] receives the map, offsets_out[n_scans+1] the start of every keyframe's points
+ * (offsets_out[n_scans] = total).  Returns ARVC_E_CAPACITY with valid offsets when capacity_points is too small
+ * (sum of the raw sizes always suffices).  Synchronises. */
+int arvc_map_build(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const double* T, const arvc_preprocess_params* p,
+                   double* xyz_out, int64_t capacity_points, int64_t* offsets_out);
 /* Parity taps.  raw_index[n_filtered]: raw indices kept by the filter, ascending.
  * voxel keys[n_points*3] (Open3D voxel index per output point) and counts[n_points]; voxel mode only.
  * nn_count[n_points]: number of neighbours used by the normal of each point (after the k / radius cut). */

@@ -506,6 +506,65 @@ int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* no
     return ARVC_OK;
 }
 
+int arvc_map_build(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const double* T, const arvc_preprocess_params* p,
+                   double* xyz_out, int64_t capacity_points, int64_t* offsets_out) {
+    if (!ctx) return ARVC_E_ARG;
+    if (n_scans < 0 || (n_scans > 0 && (!scan_ids || !T)) || !p || !offsets_out || capacity_points < 0 || (capacity_points > 0 && !xyz_out))
+        return ctx->fail(ARVC_E_ARG, "map_build: bad arguments");
+    if (n_scans > 32768) return ctx->fail(ARVC_E_ARG, "map_build: at most 32768 keyframes per call (split the batch)");
+    offsets_out[0] = 0;
+    if (n_scans == 0) return ARVC_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int64_t> uniq(scan_ids, scan_ids + n_scans);          // a keyframe may appear more than once in a map
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    int rc = arvc_scan_preprocess(ctx, (int)uniq.size(), uniq.data(), p);
+    if (rc) return rc;
+    int cap_max = 1;
+    size_t h_bytes = 0;
+    const size_t ptr_bytes = align_up(sizeof(ScanDev*) * (size_t)n_scans), t_bytes = align_up(sizeof(double) * 16 * (size_t)n_scans),
+                 off_bytes = align_up(sizeof(long long) * ((size_t)n_scans + 2));   // + total, + OR of the scans' error flags
+    char* h = reinterpret_cast<char*>(ctx->pinned_get(ptr_bytes + t_bytes + off_bytes, &h_bytes));
+    if (!h) return ctx->fail(ARVC_E_NOMEM, "map_build: pinned host allocation failed");
+    const ScanDev** hp = reinterpret_cast<const ScanDev**>(h);
+    for (int i = 0; i < n_scans; ++i) {
+        Scan* s = ctx->find(scan_ids[i]);
+        hp[i] = s->d_dev;
+        cap_max = std::max(cap_max, s->dev.cap);
+    }
+    std::memcpy(h + ptr_bytes, T, sizeof(double) * 16 * (size_t)n_scans);
+    size_t head_cap = 0;
+    char* d_head = reinterpret_cast<char*>(ctx->dev_get(ptr_bytes + t_bytes + off_bytes, &head_cap));
+    if (!d_head) { ctx->pinned_put(h, h_bytes); return ctx->fail(ARVC_E_NOMEM, "map_build: device allocation failed"); }
+    const ScanDev* const* d_scans = reinterpret_cast<const ScanDev* const*>(d_head);
+    const double* d_T = reinterpret_cast<const double*>(d_head + ptr_bytes);
+    long long* d_off = reinterpret_cast<long long*>(d_head + ptr_bytes + t_bytes);
+    long long* h_off = reinterpret_cast<long long*>(h + ptr_bytes + t_bytes);
+    auto release = [&]() { ctx->dev_put(d_head, head_cap); ctx->pinned_put(h, h_bytes); };
+    cudaError_t e = cudaMemcpyAsync(d_head, h, ptr_bytes + t_bytes, cudaMemcpyHostToDevice, ctx->L.stream);
+    run_map_build(ctx->L, d_scans, d_T, n_scans, cap_max, d_off, nullptr, 0, true);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, d_off, sizeof(long long) * ((size_t)n_scans + 2), cudaMemcpyDeviceToHost, ctx->L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->L.stream);
+    if (e != cudaSuccess || ctx->L.err != cudaSuccess) { release(); return ctx->cuda_fail(e != cudaSuccess ? e : ctx->L.err, "map_build"); }
+    for (int i = 0; i <= n_scans; ++i) offsets_out[i] = (int64_t)h_off[i];
+    const long long total = h_off[n_scans], flags = h_off[n_scans + 1];
+    if (flags & ERR_HASH_FULL) { release(); return ctx->fail(ARVC_E_CAPACITY, "hash grid overflow"); }
+    if (flags & ERR_VOXEL_RANGE) { release(); return ctx->fail(ARVC_E_CAPACITY, "voxel index outside the range implied by the filter bounds"); }
+    if (total > capacity_points) { release(); return ctx->fail(ARVC_E_CAPACITY, "map_build: output capacity too small (offsets are valid)"); }
+    if (total > 0) {
+        size_t out_cap = 0;
+        double* d_out = reinterpret_cast<double*>(ctx->dev_get(sizeof(double) * 3 * (size_t)total, &out_cap));
+        if (!d_out) { release(); return ctx->fail(ARVC_E_NOMEM, "map_build: device allocation failed"); }
+        run_map_build(ctx->L, d_scans, d_T, n_scans, cap_max, d_off, d_out, total, false);
+        e = cudaMemcpyAsync(xyz_out, d_out, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost, ctx->L.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->L.stream);
+        ctx->dev_put(d_out, out_cap);
+        if (e != cudaSuccess || ctx->L.err != cudaSuccess) { release(); return ctx->cuda_fail(e != cudaSuccess ? e : ctx->L.err, "map_build"); }
+    }
+    release();
+    return ARVC_OK;
+}
+
 int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);

@@ -131,13 +131,16 @@ class KeyFrame():
         self._filtered_cache = value
 
     def filter_radius_height(self, radii=None, heights=None):
+        self._filter_bounds = (radii, heights)
         self._preprocess(self._params(False, radii, heights, voxel=False))
         return self.pointcloud_filtered
 
     def down_sample(self):
+        """Voxel down-sampling of the cloud the last filter_radius_height() produced (keyframe.py:108-111)."""
         if self.voxel_size is None:
             return
-        self._preprocess(self._params(False))
+        radii, heights = getattr(self, "_filter_bounds", (None, None))
+        self._preprocess(self._params(False, radii, heights))
 
     def pre_process(self, method=False):
         if self.pre_processed:

@@ -97,16 +97,27 @@ class KeyFrameManager():
         H = result_type()
         return [H(np.array(r["T"])) for r in rec], rec
 
-    # ------------------------------------------------------------------ map building without the GUI (host concatenation)
+    # ------------------------------------------------------------------ map building without the GUI
     def build_map(self, global_transforms, keyframe_sampling=10, radii=None, heights=None):
+        """keyframemanager.py:154-184 as ONE device batch: every keyframe is filtered with
+        radii / heights, down-sampled when voxel_size is set, moved by its sampled global transform and written at its
+        offset of a single map array.  Returns the map as a PointCloud (the reference also opens a viewer).  Unlike
+        Open3D's in-place transform, the keyframes' own `pointcloud_filtered` stay in the sensor frame."""
         if radii is None:
             radii = [0.5, 35.0]
         if heights is None:
             heights = [-120.0, 120.0]
         sampled = [global_transforms[i] for i in range(0, len(global_transforms), keyframe_sampling)]
-        out = PointCloud()
-        for i, kf in enumerate(self.keyframes):
-            kf.filter_radius_height(radii=radii, heights=heights)
-            kf.down_sample()
-            out = out + kf.transform(T=sampled[i].array)
-        return out
+        kfs = list(self.keyframes)
+        if not kfs:
+            return PointCloud()
+        for kf in kfs:
+            kf._require_loaded()
+        T = np.array([np.asarray(sampled[i].array, dtype=np.float64) for i in range(len(kfs))])
+        xyz, offsets = runtime.get_engine().map_build([kf._scan_id for kf in kfs], T, kfs[0]._params(False, radii, heights))
+        for kf in kfs:
+            kf._filter_bounds = (radii, heights)
+            kf._preprocessed_on_device = True
+            kf._filtered_cache = None
+        self.map_offsets = offsets
+        return PointCloud(xyz)

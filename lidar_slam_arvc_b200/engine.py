@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
+    "arvc_map_build",
 ]
 
 
@@ -81,6 +82,7 @@ def load_library():
     lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
     lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
     lib.arvc_icp_trace.argtypes = [vp, c.c_int64, c.c_int64, dp, c.POINTER(IcpParams), ip, dp, dp, dp, ip, c.POINTER(ResultRecord)]
+    lib.arvc_map_build.argtypes = [vp, c.c_int, i64p, dp, c.POINTER(PreprocessParams), dp, c.c_int64, i64p]
     lib.arvc_profile_enable.argtypes = [vp, c.c_int]
     lib.arvc_profile_report.argtypes = [vp, c.c_char_p, c.c_size_t]
     lib.arvc_scan_invalidate.argtypes = [vp, c.c_int64]
@@ -131,6 +133,7 @@ class Engine:
             raise EngineError("arvc_ctx_create failed (%d): %s" % (rc, self.lib.arvc_last_error(None).decode()))
         self.h = h
         self.device = int(device)
+        self._n_raw = {}                  # raw size of every uploaded scan (output capacity of map_build)
 
     def close(self):
         if getattr(self, "h", None):
@@ -154,16 +157,20 @@ class Engine:
         if a.dtype == np.float64:
             a = np.ascontiguousarray(a)
             self._ck(self.lib.arvc_scan_upload_f64(self.h, int(scan_id), a.ctypes.data, len(a)))
+            self._n_raw[int(scan_id)] = len(a)
         else:
             a = np.ascontiguousarray(a, dtype=np.float32)
             self._ck(self.lib.arvc_scan_upload_f32(self.h, int(scan_id), a.ctypes.data, len(a)))
+            self._n_raw[int(scan_id)] = len(a)
         return a
 
     def upload_ptr(self, scan_id, ptr, n):
         self._ck(self.lib.arvc_scan_upload_f32(self.h, int(scan_id), ctypes.c_void_p(ptr), int(n)))
+        self._n_raw[int(scan_id)] = int(n)
 
     def free(self, scan_id):
         self._ck(self.lib.arvc_scan_free(self.h, int(scan_id)))
+        self._n_raw.pop(int(scan_id), None)
 
     @staticmethod
     def make_preprocess_params(min_radius=0.5, max_radius=35, min_height=-1.0, max_height=50.0, voxel_size=None,
@@ -188,6 +195,19 @@ class Engine:
         nrm = np.empty((n, 3)) if normals else None
         self._ck(self.lib.arvc_scan_get_points(self.h, int(scan_id), _dp(xyz), _dp(nrm) if normals else None))
         return (xyz, nrm) if normals else xyz
+
+    def map_build(self, scan_ids, transforms, params):
+        """KeyFrameManager.build_map (keyframemanager.py:154-184) for a batch: every scan filtered / down-sampled with
+        `params`, moved by its 4x4 and concatenated in order.  Returns (xyz [total,3] float64, offsets [n+1] int64)."""
+        ids = np.ascontiguousarray(scan_ids, dtype=np.int64).reshape(-1)
+        T = np.ascontiguousarray(transforms, dtype=np.float64).reshape(-1, 4, 4)
+        if len(T) != len(ids):
+            raise ValueError("map_build: one 4x4 transform per scan")
+        offsets = np.zeros(len(ids) + 1, dtype=np.int64)
+        cap = int(sum(self._n_raw.get(int(k), 0) for k in ids))         # the filter only removes points
+        xyz = np.empty((max(cap, 1), 3))
+        self._ck(self.lib.arvc_map_build(self.h, len(ids), _i64p(ids), _dp(T), ctypes.byref(params), _dp(xyz), cap, _i64p(offsets)))
+        return xyz[:int(offsets[-1])], offsets
 
     def get_filter_indices(self, scan_id):
         n = self.info(scan_id)["n_filtered"]

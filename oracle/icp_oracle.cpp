@@ -662,6 +662,15 @@ int orc_correspondences(const double* src, int ns, const double* tgt, int nt, co
     return K;
 }
 
+// keyframe.py:399-400 KeyFrame.transform -> Open3D PointCloud::Transform (map building, keyframemanager.py:154-184)
+void orc_transform_points(const double* pts, int n, const double* T16, double* out) {
+    for (int i = 0; i < n; ++i) {
+        double p[3] = {pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2]};
+        transform_point(T16, p);
+        out[3 * (size_t)i] = p[0]; out[3 * (size_t)i + 1] = p[1]; out[3 * (size_t)i + 2] = p[2];
+    }
+}
+
 void orc_ldlt_solve6(const double* A, const double* b, double* x) { ldlt_solve6(A, b, x); }
 void orc_vec6_to_mat4(const double* v, double* T) { vec6_to_mat4(v, T); }
 void orc_svd3(const double* A, double* U, double* s, double* V) { svd3(A, U, s, V); }

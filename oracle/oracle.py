@@ -221,6 +221,30 @@ def svd3(A):
     return U, s, V
 
 
+def transform_points(points, T):
+    """keyframe.py:399-400 (`pointcloud_filtered.transform(T)`): homogeneous product, then division by w."""
+    p = _pts(points)
+    out = np.empty_like(p)
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(4, 4)
+    lib().orc_transform_points(_d(p), len(p), _d(T), _d(out))
+    return out
+
+
+def build_map(scans_f32, transforms, voxel_size=None, radii=(0.5, 35.0), heights=(-120.0, 120.0), keyframe_sampling=1):
+    """keyframemanager.py:154-184 build_map without the GUI: per keyframe filter_radius_height(radii, heights) ->
+    down_sample -> transform(sampled_transforms[i]) -> concatenate.  Returns (points [sum,3], offsets [n+1])."""
+    sampled = [transforms[i] for i in range(0, len(transforms), keyframe_sampling)]
+    parts, offsets = [], [0]
+    for s, T in zip(scans_f32, sampled):
+        p = np.asarray(s, dtype=np.float32).astype(np.float64) if np.asarray(s).dtype == np.float32 else np.asarray(s, dtype=np.float64)
+        p = p[filter_radius_height(p, radii[0], radii[1], heights[0], heights[1])]
+        if voxel_size is not None:
+            p, _, _ = voxel_down_sample(p, voxel_size)
+        parts.append(transform_points(p, T))
+        offsets.append(offsets[-1] + len(p))
+    return (np.concatenate(parts) if parts else np.zeros((0, 3))), np.array(offsets, dtype=np.int64)
+
+
 def preprocess(points_f32, voxel_size=None, method="icppointplane", min_radius=0.5, max_radius=35, min_height=-1.0,
                max_height=50.0, normal_radius=0.3, max_nn=300):
     """keyframe.py:148-162: filter → optional voxel → normals (point-plane only).  Input is the float32 PCD

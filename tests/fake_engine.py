@@ -48,6 +48,13 @@ class OracleEngine:
         pts, nrm, _ = self.pre[int(scan_id)]
         return (pts, nrm) if normals else pts
 
+    def map_build(self, scan_ids, transforms, p):
+        self.calls.append(("map_build", len(scan_ids)))
+        self.preprocess(scan_ids, p)
+        parts = [orc.transform_points(self.pre[int(k)][0], T) for k, T in zip(scan_ids, np.asarray(transforms).reshape(-1, 4, 4))]
+        offsets = np.concatenate([[0], np.cumsum([len(x) for x in parts])]).astype(np.int64)
+        return (np.concatenate(parts) if parts else np.zeros((0, 3))), offsets
+
     def icp_batch(self, tgt_ids, src_ids, init_T, p):
         self.calls.append(("icp_batch", len(tgt_ids)))
         init_T = np.asarray(init_T, dtype=np.float64).reshape(-1, 4, 4)

@@ -362,3 +362,42 @@ def test_icp_mixed_record_types(eng, seq16, src_f64, tgt_f64):
         assert_rel(tr["result"]["rmse"], ref.inlier_rmse)
     eng.free(40)
     eng.free(41)
+
+
+@pytest.mark.parametrize("voxel", [None, 0.3])
+def test_map_build_bit_exact(eng, seq32, voxel):
+    """filter -> [voxel] -> rigid transform -> concatenation of a batch of keyframes, against the
+    oracle's restatement of keyframemanager.py:154-184 (bit-exact: same operation order, no FMA)."""
+    ids = [7000 + k for k in range(len(seq32.scans))]
+    for k, s in zip(ids, seq32.scans):
+        eng.upload(k, s)
+    eng.upload(7100, seq32.scans[1].astype(np.float64) * 1.0000001)          # float64 records
+    eng.upload(7101, np.zeros((0, 3), dtype=np.float32))                      # empty keyframe
+    order = ids + [7100, 7101, ids[0]]                                        # a keyframe may appear twice
+    scans = list(seq32.scans) + [seq32.scans[1].astype(np.float64) * 1.0000001, np.zeros((0, 3), dtype=np.float32), seq32.scans[0]]
+    rng = np.random.default_rng(5)
+    Ts = [synth.pose_matrix(*rng.uniform(-20, 20, 3), *rng.uniform(-3, 3, 3)) for _ in order]
+    p = eng.make_preprocess_params(0.5, 35.0, -120.0, 120.0, voxel_size=voxel, want_normals=False)
+    xyz, off = eng.map_build(order, Ts, p)
+    want, woff = orc.build_map(scans, Ts, voxel_size=voxel)
+    np.testing.assert_array_equal(off, woff)
+    np.testing.assert_array_equal(xyz, want)
+    assert off[-2] == off[-3]                                                 # the empty keyframe contributes nothing
+    # too small an output: error + valid offsets, nothing written past the capacity
+    import ctypes
+    buf = np.full((10, 3), -7.0)
+    o2 = np.zeros(len(order) + 1, dtype=np.int64)
+    ids_a = np.array(order, dtype=np.int64)
+    T_a = np.ascontiguousarray(Ts)
+    rc = eng.lib.arvc_map_build(eng.h, len(order), ids_a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                T_a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(p),
+                                buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 10, o2.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    assert rc != 0 and b"capacity" in eng.lib.arvc_last_error(eng.h)
+    np.testing.assert_array_equal(o2, woff)
+    assert (buf == -7.0).all()
+    # the scans stay usable for registration afterwards (re-preprocessed with the ICP parameters)
+    eng.preprocess(ids[:2], eng.make_preprocess_params())
+    r = eng.icp_batch([ids[0]], [ids[1]], seq32.relative_odo(0, 1)[None], eng.make_icp_params())
+    assert r["fitness"][0] > 0.9
+    for k in ids + [7100, 7101]:
+        eng.free(k)
