@@ -69,7 +69,7 @@ def small_loop_sequence(n_scans=68, step=0.8):
     """One and a bit laps of a 45 m loop: the last poses revisit the first ones, consecutive poses 0.8 m apart so that
     the triplet gate (1 m < d(j1, j2) < 2 m, 1 < |j1 - j2|) has solutions."""
     world = synth.World(seed=7, n_boxes=24, n_cylinders=12, outer=(20.0, 14.0), inner=(10.0, 4.0))
-    return synth.Sequence(n_scans, synth.TINY_16, world=world, step=step, workers=4)
+    return synth.Sequence(n_scans, synth.TINY_16, world=world, step=step)
 
 
 def noisy_estimate(seq, seed=3):
