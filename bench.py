@@ -339,6 +339,19 @@ def main():
         line["voxel_0p2"] = {"value": P * nv / tv, "unit": UNIT, "steps": nv, "points_per_scan": int(np.mean([eng.info(int(k))["n_points"] for k in ids[:8]])),
                              "mean_icp_updates": float(np.mean(rv["updates"])), "note": "same pairs, voxel_size 0.2 (float64 records path), wall clock"}
         eng.invalidate(ids)
+        # ---- extra: the whole sequence as one map, voxel_size 0.2, ground-truth poses, host array out
+        ppm = eng.make_preprocess_params(0.5, 35.0, -120.0, 120.0, voxel_size=0.2, want_normals=False)
+        Tm = np.stack([seq.poses[int(k)] for k in ids])
+        eng.map_build(ids, Tm, ppm)
+        tm0 = time.perf_counter()
+        for _ in range(nv):
+            eng.invalidate(ids); mxyz, moff = eng.map_build(ids, Tm, ppm)
+        tm = (time.perf_counter() - tm0) / nv
+        raw_pts = float(sum(len(seq.scans[int(k)]) for k in ids))
+        line["map_build"] = {"keyframes": len(ids), "raw_points_per_s": raw_pts / tm, "map_points": int(moff[-1]), "ms": tm * 1e3,
+                             "d2h_bytes": int(moff[-1]) * 24, "note": "filter + voxel 0.2 + transform + concatenation of the batch, "
+                             "map delivered to a pageable host array, wall clock"}
+        eng.invalidate(ids)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
