@@ -170,7 +170,7 @@ template <> struct CandEval<true> {
 // mode 1: only the points k_normals_eigen flagged as ill-conditioned: same search, then the canonical re-summation
 //         and the solve inside the warp.
 template <bool WIDE>
-__global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
+__global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
     typedef typename RecT<WIDE>::type Rec;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const ScanDev& s = scans[blockIdx.y];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
     __syncwarp();
 
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    int cnt = 0;
+    int cnt = 0, dbg_nin = -1;
     double tau_d2 = r2;      // selected <=> d2 < rq2 and (d2, idx) <= (tau_d2, tau_idx)
     int tau_idx = 0x7fffffff;
     double rq2 = r2;         // radius^2 the neighbourhood was finally searched with
@@ -320,26 +320,32 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
             // ---- pass A: bucket histogram of the in-radius candidates
             for (int b = lane; b < kBins; b += 32) hist[b] = 0;
             __syncwarp();
+            auto count_one = [&](const CandEval<WIDE>& c) {
+                if constexpr (!WIDE) {
+                    // float32 bucket coordinate: beyond the last bucket -> outside the radius; safely inside a bucket
+                    // -> count it; within 2e-3 of an edge (or in the last bucket) -> decide exactly
+                    const float u = c.d2f * bsf;
+                    if (u > (float)kBins + 2e-3f) return;
+                    const int b = (int)u;
+                    const float fr = u - (float)b;
+                    if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) { atomicAdd(&hist[b], 1); return; }
+                    const double d2 = c.exact(qx, qy, qz);
+                    if (d2 < rq2) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
+                } else {
+                    double d2 = 0;
+                    bool have = false;
+                    if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
+                }
+            };
             for (int rr = 0; rr < nruns; ++rr) {
                 const uint2 run = runs[rr];
-                for (unsigned j = run.x + lane; j < run.y; j += 32) {
-                    CandEval<WIDE> c;
-                    c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                    if constexpr (!WIDE) {
-                        // float32 bucket coordinate: beyond the last bucket -> outside the radius; safely inside a bucket
-                        // -> count it; within 2e-3 of an edge (or in the last bucket) -> decide exactly
-                        const float u = c.d2f * bsf;
-                        if (u > (float)kBins + 2e-3f) continue;
-                        const int b = (int)u;
-                        const float fr = u - (float)b;
-                        if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) { atomicAdd(&hist[b], 1); continue; }
-                        const double d2 = c.exact(qx, qy, qz);
-                        if (d2 < rq2) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
-                    } else {
-                        double d2 = 0;
-                        bool have = false;
-                        if (in_radius(c, d2, have)) atomicAdd(&hist[bucket(c, d2, have)], 1);
-                    }
+                for (unsigned j = run.x + lane; j < run.y; j += 64) {      // two records in flight per lane
+                    CandEval<WIDE> c0, c1;
+                    const bool two = j + 32 < run.y;
+                    c0.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                    if (two) c1.load(recs, j + 32, qxf, qyf, qzf, qx, qy, qz);
+                    count_one(c0);
+                    if (two) count_one(c1);
                 }
             }
             __syncwarp();
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
                 if (lane >= o) inc += t;
             }
             const int n_in = __shfl_sync(kFull, inc, 31);
+            dbg_nin = n_in;
             if (trial && n_in < np.max_nn) continue;          // the guess was too small: search the full radius
             if (n_in > np.max_nn) {
                 int before = inc - local, myb = -1, myneed = 0;
@@ -382,26 +389,32 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
             if (lane == 0) *ncand_s = 0;
             __syncwarp();
             const float u_lo = (float)min(bstar, kBins) - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bstar + 1) + 2e-3f;
-            for (int rr = 0; rr < nruns; ++rr) {
-                const uint2 run = runs[rr];
-                for (unsigned j = run.x + lane; j < run.y; j += 32) {
-                    CandEval<WIDE> c;
-                    c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                    const float u = c.d2f * bsf;
-                    if (u < u_lo) {
-                        accumulate(c.x(), c.y(), c.z());
-                    } else if (u <= u_hi) {
-                        const double d2 = c.exact(qx, qy, qz);
-                        if (d2 < rq2) {
-                            const int b = min(kBins - 1, (int)(d2 * bin_scale));
-                            if (b < bstar) {
-                                accumulate(c.x(), c.y(), c.z());
-                            } else if (b == bstar) {
-                                const int slot = atomicAdd(ncand_s, 1);
-                                if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
-                            }
+            auto take_one = [&](const CandEval<WIDE>& c, unsigned j) {
+                const float u = c.d2f * bsf;
+                if (u < u_lo) {
+                    accumulate(c.x(), c.y(), c.z());
+                } else if (u <= u_hi) {
+                    const double d2 = c.exact(qx, qy, qz);
+                    if (d2 < rq2) {
+                        const int b = min(kBins - 1, (int)(d2 * bin_scale));
+                        if (b < bstar) {
+                            accumulate(c.x(), c.y(), c.z());
+                        } else if (b == bstar) {
+                            const int slot = atomicAdd(ncand_s, 1);
+                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
                         }
                     }
+                }
+            };
+            for (int rr = 0; rr < nruns; ++rr) {
+                const uint2 run = runs[rr];
+                for (unsigned j = run.x + lane; j < run.y; j += 64) {      // two records in flight per lane
+                    CandEval<WIDE> c0, c1;
+                    const bool two = j + 32 < run.y;
+                    c0.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                    if (two) c1.load(recs, j + 32, qxf, qyf, qzf, qx, qy, qz);
+                    take_one(c0, j);
+                    if (two) take_one(c1, j + 32);
                 }
             }
             __syncwarp();
@@ -505,8 +518,8 @@ __global__ void __launch_bounds__(kNrmWarps * 32) k_normals(const ScanDev* __res
         break;
     }
 
-    if ((np.debug & 1) && lane == 0 && (p % 997) == 0)      // ARVC_DEBUG_NORMALS=1: sampled per-point search statistics
-        printf("NRM p=%d total=%d ntry=%d total_try=%d rtry=%.3f used_trial=%d nruns=%d\n", p, total, ntry, total_try, rtry, (int)(runs == runs_try), nruns);
+    if ((np.debug & 1) && lane == 0 && (p % 97) == 0)      // ARVC_DEBUG_NORMALS=1: sampled per-point search statistics
+        printf("NRM p=%d total=%d ntry=%d total_try=%d rtry=%.3f used_trial=%d nruns=%d n_in=%d\n", p, total, ntry, total_try, rtry, (int)(runs == runs_try), nruns, dbg_nin);
     cnt = warp_sum(cnt);
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
