@@ -120,6 +120,7 @@ constexpr int kCanon = 320;          // most neighbours the canonical (sorted, s
 constexpr int kScratch = kCanon * 20;  // bytes of the two overlapping layouts above
 constexpr int kTryRuns = 160;          // cells of the trial ball (6^3 = 216 before box pruning)
 constexpr int kWarpSmem = kScratch + (64 + kTryRuns) * 8;   // + cell runs, which outlive both layouts
+constexpr int kSpecFactor3 = 7;        // up to kSpecFactor3/3 * max_nn candidates: speculative single pass at the full radius
 constexpr int kDenseFactor2 = 3;       // neighbourhoods with more than kDenseFactor2/2 * max_nn candidates try a smaller radius first
 static_assert(kBins * 4 + kCand * 16 + 16 <= kScratch, "selection layout must fit");
 constexpr double kIllGap = 2e-3;     // below this relative eigen-gap the normal is recomputed in canonical order
@@ -315,7 +316,87 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             return d2 < rq2;
         };
 
+        // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
+        auto pass_b = [&](const int bstar) -> int {
+            int ncand = 0;
+            if constexpr (!WIDE) {
+                // float32 bucket coordinate u = d2f * buckets / r^2 (absolute error < 1e-3): two compares settle almost every
+                // candidate - certainly below bucket bstar (taken), certainly above it (dropped); the rest is decided exactly
+                int* ncand_s = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 16);
+                if (lane == 0) *ncand_s = 0;
+                __syncwarp();
+                const float u_lo = (float)min(bstar, kBins) - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bstar + 1) + 2e-3f;
+                auto take_one = [&](const CandEval<WIDE>& c, unsigned j) {
+                    const float u = c.d2f * bsf;
+                    if (u < u_lo) {
+                        accumulate(c.x(), c.y(), c.z());
+                    } else if (u <= u_hi) {
+                        const double d2 = c.exact(qx, qy, qz);
+                        if (d2 < rq2) {
+                            const int b = min(kBins - 1, (int)(d2 * bin_scale));
+                            if (b < bstar) {
+                                accumulate(c.x(), c.y(), c.z());
+                            } else if (b == bstar) {
+                                const int slot = atomicAdd(ncand_s, 1);
+                                if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                            }
+                        }
+                    }
+                };
+                for (int rr = 0; rr < nruns; ++rr) {
+                    const uint2 run = runs[rr];
+                    for (unsigned j = run.x + lane; j < run.y; j += 64) {      // two records in flight per lane
+                        CandEval<WIDE> c0, c1;
+                        const bool two = j + 32 < run.y;
+                        c0.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                        if (two) c1.load(recs, j + 32, qxf, qyf, qzf, qx, qy, qz);
+                        take_one(c0, j);
+                        if (two) take_one(c1, j + 32);
+                    }
+                }
+                __syncwarp();
+                ncand = *ncand_s;
+            } else {
+                for (int rr = 0; rr < nruns; ++rr) {
+                    const uint2 run = runs[rr];
+                    for (unsigned t = run.x; t < run.y; t += 32) {
+                        const unsigned j = t + lane;
+                        bool hit = false;
+                        double d2 = 0;
+                        CandEval<WIDE> c;
+                        if (j < run.y) {
+                            c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
+                            bool have = false;
+                            if (in_radius(c, d2, have)) {
+                                const int b = bstar == kBins ? 0 : bucket(c, d2, have);
+                                if (b < bstar) accumulate(c.x(), c.y(), c.z());
+                                else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
+                            }
+                        }
+                        if (bstar != kBins) {
+                            const unsigned m = __ballot_sync(kFull, hit);
+                            if (hit) {
+                                const int slot = ncand + __popc(m & ((1u << lane) - 1u));
+                                if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
+                            }
+                            ncand += __popc(m);
+                        }
+                    }
+                }
+            }
+            return ncand;
+        };
+
         int bstar = kBins, need = 0;       // buckets < bstar are taken whole; `need` more come from bucket bstar
+        // Moderately populated neighbourhoods at the full radius mostly hold <= k points inside the radius: take all
+        // of them in ONE pass and count; only when more than k turn up is the work discarded and the selection run.
+        bool settled = false;
+        if (!trial && tot > np.max_nn && 3 * tot <= kSpecFactor3 * np.max_nn) {
+            pass_b(kBins);
+            if (warp_sum(cnt) <= np.max_nn) settled = true;
+            else { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0; cnt = 0; }
+        }
+        if (settled) break;
         if (tot > np.max_nn) {
             // ---- pass A: bucket histogram of the in-radius candidates
             for (int b = lane; b < kBins; b += 32) hist[b] = 0;
@@ -380,73 +461,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             __syncwarp();
         }
 
-        // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
-        int ncand = 0;
-        if constexpr (!WIDE) {
-            // float32 bucket coordinate u = d2f * buckets / r^2 (absolute error < 1e-3): two compares settle almost every
-            // candidate - certainly below bucket bstar (taken), certainly above it (dropped); the rest is decided exactly
-            int* ncand_s = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 16);
-            if (lane == 0) *ncand_s = 0;
-            __syncwarp();
-            const float u_lo = (float)min(bstar, kBins) - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bstar + 1) + 2e-3f;
-            auto take_one = [&](const CandEval<WIDE>& c, unsigned j) {
-                const float u = c.d2f * bsf;
-                if (u < u_lo) {
-                    accumulate(c.x(), c.y(), c.z());
-                } else if (u <= u_hi) {
-                    const double d2 = c.exact(qx, qy, qz);
-                    if (d2 < rq2) {
-                        const int b = min(kBins - 1, (int)(d2 * bin_scale));
-                        if (b < bstar) {
-                            accumulate(c.x(), c.y(), c.z());
-                        } else if (b == bstar) {
-                            const int slot = atomicAdd(ncand_s, 1);
-                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
-                        }
-                    }
-                }
-            };
-            for (int rr = 0; rr < nruns; ++rr) {
-                const uint2 run = runs[rr];
-                for (unsigned j = run.x + lane; j < run.y; j += 64) {      // two records in flight per lane
-                    CandEval<WIDE> c0, c1;
-                    const bool two = j + 32 < run.y;
-                    c0.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                    if (two) c1.load(recs, j + 32, qxf, qyf, qzf, qx, qy, qz);
-                    take_one(c0, j);
-                    if (two) take_one(c1, j + 32);
-                }
-            }
-            __syncwarp();
-            ncand = *ncand_s;
-        } else {
-            for (int rr = 0; rr < nruns; ++rr) {
-                const uint2 run = runs[rr];
-                for (unsigned t = run.x; t < run.y; t += 32) {
-                    const unsigned j = t + lane;
-                    bool hit = false;
-                    double d2 = 0;
-                    CandEval<WIDE> c;
-                    if (j < run.y) {
-                        c.load(recs, j, qxf, qyf, qzf, qx, qy, qz);
-                        bool have = false;
-                        if (in_radius(c, d2, have)) {
-                            const int b = bstar == kBins ? 0 : bucket(c, d2, have);
-                            if (b < bstar) accumulate(c.x(), c.y(), c.z());
-                            else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
-                        }
-                    }
-                    if (bstar != kBins) {
-                        const unsigned m = __ballot_sync(kFull, hit);
-                        if (hit) {
-                            const int slot = ncand + __popc(m & ((1u << lane) - 1u));
-                            if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
-                        }
-                        ncand += __popc(m);
-                    }
-                }
-            }
-        }
+        const int ncand = pass_b(bstar);
         if (bstar != kBins) {
             __syncwarp();
             if (ncand <= kCand) {
