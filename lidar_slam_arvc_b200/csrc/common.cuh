@@ -36,6 +36,23 @@ __device__ __forceinline__ double sqdist(double ax, double ay, double az, double
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// t -> (t % nx, (t / nx) % ny, t / (nx * ny)) for the small cell blocks of the searches (t < 4096, nx, ny <= 64) without
+// integer division: (t + 0.5) / n is at least 0.5 / n away from an integer, far beyond the error of the float reciprocal.
+struct CellDecoder {
+    int nx, nxy;
+    float inx, inxy;
+    __device__ __forceinline__ CellDecoder(int nx_, int ny_) : nx(nx_), nxy(nx_ * ny_) {
+        inx = __frcp_rn((float)nx);
+        inxy = __frcp_rn((float)nxy);
+    }
+    __device__ __forceinline__ void operator()(int t, int& ox, int& oy, int& oz) const {
+        oz = (int)(((float)t + 0.5f) * inxy);
+        const int rem = t - oz * nxy;
+        oy = (int)(((float)rem + 0.5f) * inx);
+        ox = rem - oy * nx;
+    }
+};
+
 // ---- multi-resolution Morton hash grid ---------------------------------------------------------------
 // Level l has cubic cells of edge c0 * 2^l; a level-l cell is the Morton prefix (code >> 3l).  Because the
 // records are sorted by Morton code, every cell of every level is one contiguous run [start, end).

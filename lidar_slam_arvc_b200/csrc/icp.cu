@@ -49,9 +49,11 @@ __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int 
 
 // float32 screening threshold for a best-so-far d2 (see DESIGN.md "float32 screening"): narrow target records are
 // exact float32 values, so |d2f - d2| <= 2e-6 d2 + 3.5 sqrt(d2) e + 3 e^2 with e the rounding of the query coordinates.
+// sqrt(b) is bounded from above with one MUFU: b * rsqrt(b) (2 ulp) inflated by 1e-6, + 1e-15 for b below the clamp.
 __device__ __forceinline__ float screen_thr(double best_d2, float e) {
     const float b = __double2float_ru(best_d2);
-    return (b * (1.0f + 4e-6f) + 3.6f * e * sqrtf(b) + 3.1f * e * e) * (1.0f + 1e-6f);
+    const float s = b * rsqrtf(fmaxf(b, 1e-30f)) * (1.0f + 1e-6f) + 1e-15f;
+    return (b * (1.0f + 4e-6f) + 3.6f * e * s + 3.1f * e * e) * (1.0f + 1e-6f);
 }
 
 template <bool TW>
@@ -81,6 +83,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                   hz = min(max(cell_coord(sz, g.oz, g.inv_c0) >> l, z0), z1);
         const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);     // <= 27
         const int home = (hx - x0) + nx * ((hy - y0) + ny * (hz - z0));
+        const CellDecoder dec(nx, ny);
         int top = 0;
         // push the ball's cells, later rounds first, so that order position 0 (the home cell) ends on top
         for (int base = ((ncell - 1) / kG) * kG; base >= 0; base -= kG) {
@@ -91,7 +94,8 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
             float lbf = 0.f;
             if (t < ncell) {
                 const int c = t == 0 ? home : (t <= home ? t - 1 : t);
-                cx = x0 + c % nx; cy = y0 + (c / nx) % ny; cz = z0 + c / (nx * ny);
+                dec(c, cx, cy, cz);
+                cx += x0; cy += y0; cz += z0;
                 const double bd = box_d2(g, cx, cy, cz, cl, sx, sy, sz);
                 if (bd <= gbest * (1.0 + 1e-9) + 1e-12) {
                     valid = grid_lookup(tab, tmask, l, morton3(cx, cy, cz), st, en);
@@ -505,19 +509,21 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
             // sparse regions / jumps of the space-filling curve: the 8 queries span too many cells here, try a coarser level
             if (ncell > kUnionMax) continue;
             int nr = 0, utotal = 0;
+            const CellDecoder dec(nx, ny);
             for (int base = 0; base < ncell; base += kG) {
                 const int t = base + gl;
                 bool valid = false;
                 unsigned rs = 0, re = 0;
+                int ox = 0, oy = 0, oz = 0;
                 if (t < ncell) {
-                    const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
-                    valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(cx, cy, cz), rs, re);
+                    dec(t, ox, oy, oz);
+                    valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(x0 + ox, y0 + oy, z0 + oz), rs, re);
                 }
                 const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
                 if (valid) {
                     const int slot = nr + __popc(vm & ((1u << gl) - 1u));
                     runs[slot] = make_uint2(rs, re);
-                    rcell[slot] = (unsigned)(t % nx) | ((unsigned)((t / nx) % ny) << 8) | ((unsigned)(t / (nx * ny)) << 16);   // offsets from x0,y0,z0
+                    rcell[slot] = (unsigned)ox | ((unsigned)oy << 8) | ((unsigned)oz << 16);   // offsets from x0,y0,z0
                 }
                 nr += __popc(vm);
                 utotal += (int)(re - rs);

@@ -212,12 +212,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
 
     // ---- cells of the full radius (<= 27 at the level whose edge >= radius): lane c owns cell c
     int nfull = 0, total = 0;
+    const CellDecoder dec(nx, ny);
     for (int base = 0; base < ncell; base += 32) {      // one round unless the ball grazes a fourth cell along an axis
         const int t = base + lane;
         unsigned st = 0, en = 0;
         bool valid = false;
         if (t < ncell) {
-            const int cx = x0 + t % nx, cy = y0 + (t / nx) % ny, cz = z0 + t / (nx * ny);
+            int cx, cy, cz;
+            dec(t, cx, cy, cz);
+            cx += x0; cy += y0; cz += z0;
             const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
             const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cl)));
             const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cl)));
@@ -245,12 +248,15 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             const int fy0 = cell_coord(qy - rt, g.oy, g.inv_c0) >> Lf, fy1 = cell_coord(qy + rt, g.oy, g.inv_c0) >> Lf;
             const int fz0 = cell_coord(qz - rt, g.oz, g.inv_c0) >> Lf, fz1 = cell_coord(qz + rt, g.oz, g.inv_c0) >> Lf;
             const int fnx = fx1 - fx0 + 1, fny = fy1 - fy0 + 1, fncell = fnx * fny * (fz1 - fz0 + 1);
+            const CellDecoder fdec(fnx, fny);
             for (int base = 0; base < fncell; base += 32) {
                 const int t = base + lane;
                 unsigned st = 0, en = 0;
                 bool valid = false;
                 if (t < fncell) {
-                    const int cx = fx0 + t % fnx, cy = fy0 + (t / fnx) % fny, cz = fz0 + t / (fnx * fny);
+                    int cx, cy, cz;
+                    fdec(t, cx, cy, cz);
+                    cx += fx0; cy += fy0; cz += fz0;
                     const double bx0 = g.ox + cx * cf, by0 = g.oy + cy * cf, bz0 = g.oz + cz * cf;
                     const double ddx = fmax(0.0, fmax(bx0 - qx, qx - (bx0 + cf)));
                     const double ddy = fmax(0.0, fmax(by0 - qy, qy - (by0 + cf)));
