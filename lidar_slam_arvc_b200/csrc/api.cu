@@ -396,7 +396,8 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     for (Scan* s : todo) {
         const bool wide = s->f64 || voxel_on;
         unsigned tcap = 1024;
-        while (tcap < (c0 < 0.12 ? 8u : 4u) * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;      // finer grids occupy more cells
+        const unsigned tfac = getenv("ARVC_TABLE_FACTOR") ? (unsigned)atoi(getenv("ARVC_TABLE_FACTOR")) : (c0 < 0.12 ? 8u : 4u);
+        while (tcap < tfac * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;      // finer grids occupy more cells
         if (s->slab) { cudaFreeAsync(s->slab, ctx->L.stream); s->slab = nullptr; }
         SlabPlanner pp;
         plan_persistent(pp, *s, wide, voxel_on, tcap);
@@ -659,7 +660,7 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             int* prev = P.take<int>(cap);
             float* lb2 = P.take<float>(cap);
             unsigned char* cpass = P.take<unsigned char>(cap);
-            int* list = P.take<int>(cap + (cap + 255) / 256 * 8);   // + padding per block of the select kernel
+            int* list = P.take<int>(cap + (cap + 255) / 256 * 32);   // + padding per block of the select kernel
             int* ct = trace ? P.take<int>(cap * passes) : nullptr;
             double* stt = trace ? P.take<double>((size_t)passes * 18) : nullptr;
             if (pass) {

@@ -29,7 +29,8 @@ struct Best { double d2; int idx; int pos; };
 //   * when the level's ball is exhausted and the best is not yet certified, the search moves one level up.
 // The result is the exact minimiser of (d2, cloud index): d2 evaluated exactly as the oracle evaluates it.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kG = 8;            // lanes per query
+constexpr int kG = 8;            // lanes per query (16: unions outgrow the caps, 15x slower)
+constexpr unsigned kGMask = kG == 32 ? 0xffffffffu : ((1u << kG) - 1u);
 constexpr int kBigRun = 160;     // longer runs are expanded into their children instead of scanned
 constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                     lbf = __double2float_rd(bd);
                 }
             }
-            const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+            const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kGMask;
             if (valid) {
                 const int pos = top + __popc(vm & ~((2u << gl) - 1u));
                 stk[pos] = make_uint4(st, en, (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20), (unsigned)l);
@@ -168,7 +169,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                 bool valid = false;
                 unsigned st = 0, en = 0;
                 if (bd <= gbest * (1.0 + 1e-9) + 1e-12) valid = grid_lookup(tab, tmask, el - 1, morton3(ccx, ccy, ccz), st, en);
-                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kGMask;
                 if (valid) {
                     const int pos = top + __popc(vm & ~((2u << gl) - 1u));
                     stk[pos] = make_uint4(st, en, (unsigned)ccx | ((unsigned)ccy << 10) | ((unsigned)ccz << 20), (unsigned)(el - 1));
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                     dec(t, ox, oy, oz);
                     valid = grid_lookup(tgt.table, tgt.table_mask, lu, morton3(x0 + ox, y0 + oy, z0 + oz), rs, re);
                 }
-                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & 0xffu;
+                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kGMask;
                 if (valid) {
                     const int slot = nr + __popc(vm & ((1u << gl) - 1u));
                     runs[slot] = make_uint2(rs, re);

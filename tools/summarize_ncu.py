@@ -68,5 +68,46 @@ def full(path):
     print("# dram traffic per launch (bytes):", json.dumps(traffic))
 
 
+def traffic(path, n_scans=9):
+    """profiles/traffic.json from a --set full capture of tools/prof_target.py <n_scans> (k_normals + k_icp_search passes)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def num(r, k):
+        v = float(r[idx[k]].replace(",", ""))
+        u = units[idx[k]].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+
+    def pcts(r):
+        return {"issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fma_pipe_pct": num(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct": num(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "l2_hit_pct": num(r, "lts__t_sector_hit_rate.pct"),
+                "dram_pct_of_peak": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
+
+    res = {"source": "ncu --set full of tools/prof_target.py %d (%s)" % (n_scans, path.split("/")[-1])}
+    nrm = [r for r in rows[2:] if "k_normals<" in r[idx["Kernel Name"]]]
+    srch = [r for r in rows[2:] if "k_icp_search" in r[idx["Kernel Name"]]]
+    if nrm:
+        r = nrm[0]
+        d = pcts(r)
+        d["dram_bytes_per_scan"] = (num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")) / n_scans
+        d["warp_instructions"] = num(r, "smsp__inst_executed.sum")
+        d["registers"] = num(r, "launch__registers_per_thread")
+        res["normals"] = d
+    if srch:
+        per = [(num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")) / (n_scans - 1) for r in srch]
+        d = {"dram_bytes_per_pair_pass": sum(per) / len(per), "by_pass": per, "registers": num(srch[0], "launch__registers_per_thread"),
+             "warp_instructions_by_pass": [num(r, "smsp__inst_executed.sum") for r in srch],
+             "active_lanes_by_pass": [num(r, "smsp__thread_inst_executed_per_inst_executed.ratio") for r in srch]}
+        for k in pcts(srch[0]):
+            d[k] = [pcts(r)[k] for r in srch]
+        res["icp_pass"] = d
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
