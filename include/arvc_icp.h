@@ -100,6 +100,17 @@ int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* no
  * (sum of the raw sizes always suffices).  Synchronises. */
 int arvc_map_build(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const double* T, const arvc_preprocess_params* p,
                    double* xyz_out, int64_t capacity_points, int64_t* offsets_out);
+/* 'icp2planes' preprocessing (keyframe.py:164-189), on the preprocessed cloud of a scan:
+ * KeyFrame.calculate_plane (keyframe.py:417-436): plane a x + b y + c z + d = 0 (unit normal) through the points with
+ * z < max_z (-0.5), RANSAC with 3-point hypotheses (`iterations` 1000, inlier distance `dist_threshold` 0.01).  Open3D's
+ * RANSAC is unseeded; here the samples are a hash of (seed, iteration), so equal inputs give equal planes.  Synchronises.
+ * KeyFrame.segment_plane (keyframe.py:438-461): points with |a x + b y + c z + d| / sqrt(a^2+b^2+c^2) < threshold (0.4)
+ * become the raw cloud of scan `near_id`, the others of `far_id` (float64, order preserved: select_by_index /
+ * invert=True); both are then preprocessed like any uploaded scan.  Synchronises. */
+int arvc_scan_fit_plane(arvc_ctx* ctx, int64_t scan_id, double max_z, double dist_threshold, int iterations, uint64_t seed,
+                        double* plane_out /* [4] */, int32_t* n_inliers);
+int arvc_scan_split_plane(arvc_ctx* ctx, int64_t src_id, const double* plane /* [4] */, double threshold, int64_t near_id, int64_t far_id,
+                          int32_t* n_near, int32_t* n_far);
 /* Parity taps.  raw_index[n_filtered]: raw indices kept by the filter, ascending.
  * voxel keys[n_points*3] (Open3D voxel index per output point) and counts[n_points]; voxel mode only.
  * nn_count[n_points]: number of neighbours used by the normal of each point (after the k / radius cut). */

@@ -566,6 +566,81 @@ int arvc_map_build(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const do
     return ARVC_OK;
 }
 
+int arvc_scan_fit_plane(arvc_ctx* ctx, int64_t scan_id, double max_z, double dist_threshold, int iterations, uint64_t seed,
+                        double* plane_out, int32_t* n_inliers) {
+    if (!ctx) return ARVC_E_ARG;
+    if (!plane_out || iterations < 1 || iterations > 65535 || !(dist_threshold > 0)) return ctx->fail(ARVC_E_ARG, "scan_fit_plane: bad arguments");
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_fit_plane: scan not preprocessed");
+    CK(cudaSetDevice(ctx->device));
+    const size_t cap = (size_t)std::max(s->dev.cap, 1);
+    const size_t orig_b = align_up(sizeof(double) * 3 * cap), score_b = align_up(sizeof(int) * (size_t)iterations), res_b = align_up(sizeof(double) * 5);
+    size_t got = 0;
+    char* d = reinterpret_cast<char*>(ctx->dev_get(orig_b + score_b + res_b, &got));
+    if (!d) return ctx->fail(ARVC_E_NOMEM, "scan_fit_plane: device allocation failed");
+    double* d_res = reinterpret_cast<double*>(d + orig_b + score_b);
+    run_plane_fit(ctx->L, s->d_dev, s->dev.cap, reinterpret_cast<double*>(d), reinterpret_cast<int*>(d + orig_b), d_res, max_z, dist_threshold,
+                  iterations, (unsigned long long)seed);
+    double h_res[5] = {0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h_res, d_res, sizeof(h_res), cudaMemcpyDeviceToHost, ctx->L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->L.stream);
+    ctx->dev_put(d, got);
+    if (e != cudaSuccess || ctx->L.err != cudaSuccess) return ctx->cuda_fail(e != cudaSuccess ? e : ctx->L.err, "scan_fit_plane");
+    for (int k = 0; k < 4; ++k) plane_out[k] = h_res[k];
+    if (n_inliers) *n_inliers = (int32_t)h_res[4];
+    if (h_res[4] < 3) return ctx->fail(ARVC_E_STATE, "scan_fit_plane: fewer than three usable points below max_z");
+    return ARVC_OK;
+}
+
+int arvc_scan_split_plane(arvc_ctx* ctx, int64_t src_id, const double* plane, double threshold, int64_t near_id, int64_t far_id,
+                          int32_t* n_near, int32_t* n_far) {
+    if (!ctx) return ARVC_E_ARG;
+    if (!plane || near_id == far_id || near_id == src_id || far_id == src_id) return ctx->fail(ARVC_E_ARG, "scan_split_plane: bad arguments");
+    Scan* s = ctx->find(src_id);
+    if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_split_plane: scan not preprocessed");
+    const double norm = std::sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);    // np.sqrt(a*a + b*b + c*c)
+    if (!(norm > 0)) return ctx->fail(ARVC_E_ARG, "scan_split_plane: degenerate plane");
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t id : {near_id, far_id}) {
+        Scan* old = ctx->find(id);
+        if (old) { release_scan(ctx, old); ctx->scans.erase(id); }
+    }
+    const size_t cap = (size_t)std::max(s->dev.cap, 1);
+    const size_t orig_b = align_up(sizeof(double) * 3 * cap), blk_b = align_up(sizeof(int) * ((cap + 1023) / 1024 + 8)), cnt_b = align_up(sizeof(int) * 2);
+    size_t got = 0;
+    char* d = reinterpret_cast<char*>(ctx->dev_get(orig_b + blk_b + cnt_b, &got));
+    if (!d) return ctx->fail(ARVC_E_NOMEM, "scan_split_plane: device allocation failed");
+    void *d_near = nullptr, *d_far = nullptr;
+    cudaError_t e = cudaMallocAsync(&d_near, sizeof(double) * 3 * cap, ctx->L.stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_far, sizeof(double) * 3 * cap, ctx->L.stream);
+    int h_cnt[2] = {0, 0};
+    if (e == cudaSuccess) {
+        int* d_cnt = reinterpret_cast<int*>(d + orig_b + blk_b);
+        run_plane_split(ctx->L, s->d_dev, s->dev.cap, reinterpret_cast<double*>(d), reinterpret_cast<int*>(d + orig_b), reinterpret_cast<double*>(d_near),
+                        reinterpret_cast<double*>(d_far), d_cnt, plane, norm, threshold);
+        e = cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->L.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->L.stream);
+    }
+    ctx->dev_put(d, got);
+    if (e != cudaSuccess || ctx->L.err != cudaSuccess) {
+        if (d_near) cudaFreeAsync(d_near, ctx->L.stream);
+        if (d_far) cudaFreeAsync(d_far, ctx->L.stream);
+        return ctx->cuda_fail(e != cudaSuccess ? e : ctx->L.err, "scan_split_plane");
+    }
+    const int64_t ids[2] = {near_id, far_id};
+    void* bufs[2] = {d_near, d_far};
+    for (int k = 0; k < 2; ++k) {
+        auto ns = std::make_unique<Scan>();
+        ns->id = ids[k]; ns->n_raw = h_cnt[k]; ns->f64 = true;
+        if (h_cnt[k] > 0) ns->d_raw = bufs[k];
+        else cudaFreeAsync(bufs[k], ctx->L.stream);
+        ctx->scans[ids[k]] = std::move(ns);
+    }
+    if (n_near) *n_near = h_cnt[0];
+    if (n_far) *n_far = h_cnt[1];
+    return ARVC_OK;
+}
+
 int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);

@@ -104,6 +104,10 @@ void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_ma
                     bool voxel_on);
 void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow);
 void run_icp(Launcher& L, const PairDev* d_pairs, int n_pairs, int src_cap_max, const IcpParams& ip, int combos_mask);
+void run_plane_fit(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_score, double* d_result, double max_z, double thr,
+                   int iters, unsigned long long seed);
+void run_plane_split(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_blk, double* d_near, double* d_far, int* d_counts2,
+                     const double* plane, double norm, double thr);
 void run_map_build(Launcher& L, const ScanDev* const* d_scans, const double* d_T, int n_scans, int cap_max, long long* d_offsets,
                    double* d_out, long long capacity, bool offsets_only);
 

@@ -43,6 +43,14 @@ class PointCloud:
         return len(self.points)
 
 
+def merge_two_planes(T_ground, T_non_ground):
+    """keyframe.py:282-292: t2v(n=3) of both results; tx, ty, gamma from the non-ground one, tz, alpha, beta from the ground."""
+    H = result_type()
+    t1 = H(np.asarray(T_ground)).t2v(n=3)
+    t2 = H(np.asarray(T_non_ground)).t2v(n=3)
+    return H(np.array([t2[0], t2[1], t1[2]]), [float(t1[3]), float(t1[4]), float(t2[5])])
+
+
 class KeyFrame():
     def __init__(self, directory, scan_time, voxel_size):
         self.directory = directory
@@ -50,8 +58,6 @@ class KeyFrame():
         self.voxel_size = voxel_size
         self.fpfh_threshold = 5
         self.pointcloud = None
-        self.pointcloud_ground_plane = None
-        self.pointcloud_non_ground_plane = None
         self.pointcloud_fpfh = None
         self.voxel_size_normals_ground_plane = 0.5
         self.voxel_size_normals = 0.3            # the radius actually used for normals (keyframe.py:33)
@@ -66,6 +72,12 @@ class KeyFrame():
         self._filtered_cache = None
         self._on_device = False
         self._preprocessed_on_device = False
+        # 'icp2planes': the ground / non-ground parts live on the device as two more scans
+        self._scan_id_ground = runtime.new_scan_id()
+        self._scan_id_non_ground = runtime.new_scan_id()
+        self._planes_on_device = False
+        self._plane_clouds = [None, None]
+        self.plane_seed = 0                      # extension: seed of the reproducible RANSAC (Open3D's is unseeded)
 
     # ------------------------------------------------------------------ load / unload
     def load_pointcloud(self):
@@ -89,9 +101,31 @@ class KeyFrame():
         self._preprocessed_on_device = False
         self._filtered_cache = None
         self.pointcloud = None
-        self.pointcloud_ground_plane = None
-        self.pointcloud_non_ground_plane = None
+        self._drop_planes()
         self.pointcloud_fpfh = None
+
+    def _drop_planes(self):
+        if self._planes_on_device:
+            runtime.get_engine().free(self._scan_id_ground)
+            runtime.get_engine().free(self._scan_id_non_ground)
+        self._planes_on_device = False
+        self._plane_clouds = [None, None]
+
+    def _plane_cloud(self, which):
+        if not self._planes_on_device:
+            return None
+        if self._plane_clouds[which] is None:
+            pts, nrm = runtime.get_engine().get_points((self._scan_id_ground, self._scan_id_non_ground)[which], normals=True)
+            self._plane_clouds[which] = PointCloud(pts, nrm)
+        return self._plane_clouds[which]
+
+    @property
+    def pointcloud_ground_plane(self):
+        return self._plane_cloud(0)
+
+    @property
+    def pointcloud_non_ground_plane(self):
+        return self._plane_cloud(1)
 
     # ------------------------------------------------------------------ preprocessing
     def _params(self, want_normals, radii=None, heights=None, voxel=True):
@@ -150,14 +184,62 @@ class KeyFrame():
             self.preprocess_icp_point_point()
         elif method == 'icppointplane':
             self.preprocess_icp_point_plane()
-        elif method in ('icp2planes', 'fpfh'):
-            raise NotImplementedError("method '%s' is outside the B200 hot path (Open3D RANSAC based)" % method)
+        elif method == 'icp2planes':
+            self.preprocess_icp2planes()
+        elif method == 'fpfh':
+            raise NotImplementedError("method 'fpfh' is outside the B200 hot path (Open3D global registration)")
 
     def preprocess_icp_point_point(self):
         self._preprocess(self._params(False))
 
     def preprocess_icp_point_plane(self):
         self._preprocess(self._params(True))
+
+    def preprocess_icp2planes(self):
+        """keyframe.py:164-189: filter -> [voxel] -> normals, ground-plane model, split into the points within 0.4 m of
+        the plane and the rest, normals of both parts (radius 0.5 / max_nn_gd on the ground, 0.3 / max_nn elsewhere).
+        A plane_model assigned by the caller beforehand is kept (the reference hints at a fixed model, keyframe.py:436)."""
+        self._preprocess(self._params(True))
+        if self.plane_model is None:
+            self.plane_model = self.calculate_plane()
+        self.segment_plane(self.plane_model, _download=False)
+        eng = runtime.get_engine()
+        for sid, radius, max_nn in ((self._scan_id_ground, self.voxel_size_normals_ground_plane, ICP_PARAMETERS.max_nn_gd),
+                                    (self._scan_id_non_ground, self.voxel_size_normals, ICP_PARAMETERS.max_nn)):
+            p = Engine.make_preprocess_params(0.0, self.max_radius, self.min_height, self.max_height, None, radius, max_nn, True,
+                                              grid_max_dist=ICP_PARAMETERS.distance_threshold)
+            p.min_radius2 = -1.0          # the parts already passed the filter: nothing may be dropped a second time
+            eng.preprocess([sid], p)
+
+    def calculate_plane(self, pcd=None, height=-0.5, thresholdA=0.01):
+        """keyframe.py:417-436: ground plane [a, b, c, d] from the filtered points below `height` (RANSAC, 1000 iterations,
+        inlier distance thresholdA) - reproducible for a given `plane_seed`."""
+        if pcd is not None:
+            raise NotImplementedError("calculate_plane works on this keyframe's filtered cloud")
+        if not self._preprocessed_on_device:
+            raise RuntimeError("pre_process / filter_radius_height first")
+        plane_model, _ = runtime.get_engine().fit_plane(self._scan_id, height, thresholdA, 1000, self.plane_seed)
+        a, b, c, d = plane_model
+        print(f"Plane model calculated: {a:.2f}x + {b:.2f}y + {c:.2f}z + {d:.2f} = 0")
+        return plane_model
+
+    def segment_plane(self, plane_model, pcd=None, thresholdB=0.4, _download=True):
+        """keyframe.py:438-461: (points within thresholdB of the plane, the others), order preserved."""
+        if pcd is not None:
+            raise NotImplementedError("segment_plane works on this keyframe's filtered cloud")
+        if not self._preprocessed_on_device:
+            raise RuntimeError("pre_process / filter_radius_height first")
+        self._drop_planes()
+        eng = runtime.get_engine()
+        eng.split_plane(self._scan_id, plane_model, thresholdB, self._scan_id_ground, self._scan_id_non_ground)
+        self._planes_on_device = True
+        if not _download:
+            return None
+        p = Engine.make_preprocess_params(0.0, self.max_radius, self.min_height, self.max_height, None, want_normals=False)
+        p.min_radius2 = -1.0
+        eng.preprocess([self._scan_id_ground, self._scan_id_non_ground], p)
+        out = (PointCloud(eng.get_points(self._scan_id_ground)), PointCloud(eng.get_points(self._scan_id_non_ground)))
+        return out
 
     # ------------------------------------------------------------------ registration
     def local_registration_simple(self, other, initial_transform, option='pointpoint'):
@@ -184,7 +266,21 @@ class KeyFrame():
         return result_type()(np.array(rec["T"]))
 
     def local_registration_two_planes(self, other, initial_transform):
-        raise NotImplementedError("icp2planes is outside the B200 hot path (SURVEY.md §8 f-2)")
+        """keyframe.py:262-295: point-to-plane ICP of the ground parts and of the non-ground parts (one device batch of two
+        pairs); x, y, gamma come from the non-ground solution, z, alpha, beta from the ground solution."""
+        print("Apply point-to-plane ICP. Local registration in two phases")
+        if initial_transform is None:
+            initial_transform = np.eye(4)
+        if not (self._planes_on_device and other._planes_on_device):
+            raise RuntimeError("pre_process('icp2planes') both keyframes before registering them")
+        eng = runtime.get_engine()
+        ip = eng.make_icp_params(P2PLANE, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
+                                 ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)
+        init = np.asarray(initial_transform, dtype=np.float64)
+        rec = eng.icp_batch([self._scan_id_ground, self._scan_id_non_ground], [other._scan_id_ground, other._scan_id_non_ground],
+                            np.stack([init, init]), ip)
+        self.last_result = rec[1]
+        return merge_two_planes(np.array(rec[0]["T"]), np.array(rec[1]["T"]))
 
     def global_registration(self, other):
         raise NotImplementedError("fpfh global registration is outside the B200 hot path")

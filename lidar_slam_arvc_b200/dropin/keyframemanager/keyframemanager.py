@@ -8,7 +8,7 @@ of the hot path.  Extension for batched callers (loop closing, SURVEY.md §8 f-1
 import numpy as np
 
 from config import ICP_PARAMETERS
-from keyframemanager.keyframe import KeyFrame, PointCloud
+from keyframemanager.keyframe import KeyFrame, PointCloud, merge_two_planes
 from lidar_slam_arvc_b200 import runtime
 from lidar_slam_arvc_b200.engine import P2P, P2PLANE
 from lidar_slam_arvc_b200.homogeneousmatrix import result_type
@@ -68,11 +68,15 @@ class KeyFrameManager():
     # ------------------------------------------------------------------ batched extensions
     def pre_process_many(self, indices):
         """pre_process() of many keyframes in one device batch (same results as calling pre_process one by one)."""
-        if self.method not in ('icppointpoint', 'icppointplane'):
-            raise NotImplementedError("batched preprocessing supports icppointpoint / icppointplane")
         kfs = [self.keyframes[i] for i in indices]
         if not kfs:
             return
+        if self.method == 'icp2planes':                 # plane model + split are per keyframe
+            for kf in kfs:
+                kf.pre_process(method=self.method)
+            return
+        if self.method not in ('icppointpoint', 'icppointplane'):
+            raise NotImplementedError("batched preprocessing supports icppointpoint / icppointplane / icp2planes")
         for kf in kfs:
             kf._require_loaded()
         runtime.get_engine().preprocess([kf._scan_id for kf in kfs], kfs[0]._params(self.method == 'icppointplane'))
@@ -83,9 +87,21 @@ class KeyFrameManager():
     def compute_transformations(self, pairs, Tijs):
         """[(i, j), ...] and initial guesses -> list of iTj, one device batch.  Each keyframe's `last_result`-style record
         is returned alongside: (transforms, records)."""
-        if self.method not in ('icppointpoint', 'icppointplane'):
-            raise NotImplementedError("batched registration supports icppointpoint / icppointplane")
         eng = runtime.get_engine()
+        if self.method == 'icp2planes':                 # two point-to-plane problems per pair, still one batch
+            ip = eng.make_icp_params(P2PLANE, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
+                                     ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)
+            tg, sr, init = [], [], []
+            for (i, j), T in zip(pairs, Tijs):
+                a = getattr(T, "array", T)
+                a = np.eye(4) if a is None else np.asarray(a, dtype=np.float64)
+                tg += [self.keyframes[i]._scan_id_ground, self.keyframes[i]._scan_id_non_ground]
+                sr += [self.keyframes[j]._scan_id_ground, self.keyframes[j]._scan_id_non_ground]
+                init += [a, a]
+            rec = eng.icp_batch(tg, sr, np.array(init).reshape(-1, 4, 4), ip)
+            return [merge_two_planes(np.array(rec[2 * k]["T"]), np.array(rec[2 * k + 1]["T"])) for k in range(len(pairs))], rec
+        if self.method not in ('icppointpoint', 'icppointplane'):
+            raise NotImplementedError("batched registration supports icppointpoint / icppointplane / icp2planes")
         method = P2P if self.method == 'icppointpoint' else P2PLANE
         ip = eng.make_icp_params(method, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
                                  ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
-    "arvc_map_build",
+    "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane",
 ]
 
 
@@ -83,6 +83,8 @@ def load_library():
     lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
     lib.arvc_icp_trace.argtypes = [vp, c.c_int64, c.c_int64, dp, c.POINTER(IcpParams), ip, dp, dp, dp, ip, c.POINTER(ResultRecord)]
     lib.arvc_map_build.argtypes = [vp, c.c_int, i64p, dp, c.POINTER(PreprocessParams), dp, c.c_int64, i64p]
+    lib.arvc_scan_fit_plane.argtypes = [vp, c.c_int64, c.c_double, c.c_double, c.c_int, c.c_uint64, dp, ip]
+    lib.arvc_scan_split_plane.argtypes = [vp, c.c_int64, dp, c.c_double, c.c_int64, c.c_int64, ip, ip]
     lib.arvc_profile_enable.argtypes = [vp, c.c_int]
     lib.arvc_profile_report.argtypes = [vp, c.c_char_p, c.c_size_t]
     lib.arvc_scan_invalidate.argtypes = [vp, c.c_int64]
@@ -208,6 +210,23 @@ class Engine:
         xyz = np.empty((max(cap, 1), 3))
         self._ck(self.lib.arvc_map_build(self.h, len(ids), _i64p(ids), _dp(T), ctypes.byref(params), _dp(xyz), cap, _i64p(offsets)))
         return xyz[:int(offsets[-1])], offsets
+
+    def fit_plane(self, scan_id, max_z=-0.5, dist_threshold=0.01, iterations=1000, seed=0):
+        """KeyFrame.calculate_plane (keyframe.py:417-436) on the preprocessed cloud: ([a, b, c, d], inliers)."""
+        pl = np.zeros(4)
+        n_in = ctypes.c_int32()
+        self._ck(self.lib.arvc_scan_fit_plane(self.h, int(scan_id), float(max_z), float(dist_threshold), int(iterations), int(seed),
+                                              _dp(pl), ctypes.byref(n_in)))
+        return pl, n_in.value
+
+    def split_plane(self, src_id, plane_model, threshold, near_id, far_id):
+        """KeyFrame.segment_plane (keyframe.py:438-461): two new scans (near the plane / the rest), returns their sizes."""
+        pl = np.ascontiguousarray(plane_model, dtype=np.float64).reshape(4)
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self.lib.arvc_scan_split_plane(self.h, int(src_id), _dp(pl), float(threshold), int(near_id), int(far_id),
+                                                ctypes.byref(a), ctypes.byref(b)))
+        self._n_raw[int(near_id)], self._n_raw[int(far_id)] = a.value, b.value
+        return a.value, b.value
 
     def get_filter_indices(self, scan_id):
         n = self.info(scan_id)["n_filtered"]

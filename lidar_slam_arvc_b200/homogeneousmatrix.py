@@ -53,6 +53,24 @@ def rot2euler(R):
     return _wrap(np.array(sols[0])), _wrap(np.array(sols[1]))
 
 
+def euler2rot(abg):
+    """R = Rx(alpha) Ry(beta) Rz(gamma), the inverse of rot2euler (reference artelib/tools.py:226-238)."""
+    ca, cb, cg = np.cos(abg[0]), np.cos(abg[1]), np.cos(abg[2])
+    sa, sb, sg = np.sin(abg[0]), np.sin(abg[1]), np.sin(abg[2])
+    Rx = np.array([[1.0, 0.0, 0.0], [0.0, ca, -sa], [0.0, sa, ca]])
+    Ry = np.array([[cb, 0.0, sb], [0.0, 1.0, 0.0], [-sb, 0.0, cb]])
+    Rz = np.array([[cg, -sg, 0.0], [sg, cg, 0.0], [0.0, 0.0, 1.0]])
+    return Rx @ Ry @ Rz
+
+
+def quaternion2rot(Q):
+    """Unit quaternion [qw, qx, qy, qz] -> rotation matrix."""
+    w, x, y, z = (float(v) for v in Q)
+    return np.array([[1 - 2 * y ** 2 - 2 * z ** 2, 2 * x * y - 2 * z * w, 2 * x * z + 2 * y * w],
+                     [2 * x * y + 2 * z * w, 1 - 2 * x ** 2 - 2 * z ** 2, 2 * y * z - 2 * x * w],
+                     [2 * x * z - 2 * y * w, 2 * y * z + 2 * x * w, 1 - 2 * x ** 2 - 2 * y ** 2]])
+
+
 class Euler:
     """Minimal stand-in of artelib.euler.Euler: the angles live in `.abg`."""
     def __init__(self, abg):
@@ -69,8 +87,15 @@ class HomogeneousMatrix:
         elif len(args) == 1:
             a = args[0]
             self.array = a.toarray() if isinstance(a, HomogeneousMatrix) else (a if isinstance(a, np.ndarray) else np.array(a))
+        elif len(args) == 2:
+            # (position, orientation): orientation = XYZ Euler angles as a list / array / object with `.abg`
+            position, orientation = args
+            abg = np.asarray(getattr(orientation, "abg", orientation), dtype=np.float64).reshape(3)
+            self.array = np.eye(4)
+            self.array[:3, :3] = euler2rot(abg)
+            self.array[:3, 3] = np.asarray(getattr(position, "array", position), dtype=np.float64).reshape(3)
         else:
-            raise TypeError("HomogeneousMatrix(position, orientation) needs the reference's artelib package")
+            raise TypeError("HomogeneousMatrix(), HomogeneousMatrix(array) or HomogeneousMatrix(position, euler)")
 
     def __str__(self):
         return str(self.array)
@@ -114,7 +139,7 @@ class HomogeneousMatrix:
     def t2v(self, n=2):
         if n == 2:
             return np.array([self.array[0, 3], self.array[1, 3], np.arctan2(self.array[1, 0], self.array[0, 0])])
-        e = rot2euler(self.array)[0]
+        e = rot2euler(quaternion2rot(self.Q()))[0]      # via the quaternion, like the reference's t2v (homogeneousmatrix.py:95-107)
         return np.array([self.array[0, 3], self.array[1, 3], self.array[2, 3], e[0], e[1], e[2]])
 
 

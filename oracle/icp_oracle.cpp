@@ -671,6 +671,56 @@ void orc_transform_points(const double* pts, int n, const double* T16, double* o
     }
 }
 
+// keyframe.py:417-436 calculate_plane -> Open3D segment_plane(distance_threshold, ransac_n=3, num_iterations): RANSAC over
+// the points with z < max_z.  Open3D draws its samples from an unseeded generator (irreproducible by design); the
+// convention fixed here and in csrc/plane.cu: sample t of hypothesis h is splitmix64(seed, h, t) % n (rejecting points
+// above max_z and duplicates, 64 tries), the hypothesis with most inliers wins, lowest h on ties, unit normal.
+static unsigned long long plane_hash(unsigned long long seed, unsigned long long a, unsigned long long b) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (a + 1) + 0xBF58476D1CE4E5B9ull * (b + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static bool plane_hypothesis(const double* pts, int n, double max_z, unsigned long long seed, int h, double* pl) {
+    int pick[3], got = 0;
+    for (int t = 0; t < 64 && got < 3; ++t) {
+        const int j = (int)(plane_hash(seed, (unsigned long long)h, (unsigned long long)t) % (unsigned long long)n);
+        if (!(pts[3 * (size_t)j + 2] < max_z)) continue;
+        bool dup = false;
+        for (int k = 0; k < got; ++k) dup |= pick[k] == j;
+        if (!dup) pick[got++] = j;
+    }
+    if (got < 3) return false;
+    const double *p0 = pts + 3 * (size_t)pick[0], *p1 = pts + 3 * (size_t)pick[1], *p2 = pts + 3 * (size_t)pick[2];
+    const double ux = p1[0] - p0[0], uy = p1[1] - p0[1], uz = p1[2] - p0[2];
+    const double vx = p2[0] - p0[0], vy = p2[1] - p0[1], vz = p2[2] - p0[2];
+    const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (!(len > 1e-12)) return false;
+    pl[0] = nx / len; pl[1] = ny / len; pl[2] = nz / len;
+    pl[3] = -(pl[0] * p0[0] + pl[1] * p0[1] + pl[2] * p0[2]);
+    return true;
+}
+int orc_fit_plane(const double* pts, int n, double max_z, double thr, int iterations, unsigned long long seed, double* plane4) {
+    int best_cnt = 0, best_h = -1;
+    std::vector<int> score(iterations, 0);
+    #pragma omp parallel for schedule(dynamic, 8)
+    for (int h = 0; h < iterations; ++h) {
+        double pl[4];
+        if (n < 3 || !plane_hypothesis(pts, n, max_z, seed, h, pl)) continue;
+        int c = 0;
+        for (int i = 0; i < n; ++i) {
+            const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+            if (z < max_z && std::fabs(pl[0] * x + pl[1] * y + pl[2] * z + pl[3]) < thr) ++c;
+        }
+        score[h] = c;
+    }
+    for (int h = 0; h < iterations; ++h) if (score[h] > best_cnt) { best_cnt = score[h]; best_h = h; }
+    plane4[0] = plane4[1] = plane4[2] = plane4[3] = 0;
+    if (best_h >= 0) plane_hypothesis(pts, n, max_z, seed, best_h, plane4);
+    return best_cnt;
+}
+
 void orc_ldlt_solve6(const double* A, const double* b, double* x) { ldlt_solve6(A, b, x); }
 void orc_vec6_to_mat4(const double* v, double* T) { vec6_to_mat4(v, T); }
 void orc_svd3(const double* A, double* U, double* s, double* V) { svd3(A, U, s, V); }

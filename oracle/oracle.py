@@ -245,6 +245,37 @@ def build_map(scans_f32, transforms, voxel_size=None, radii=(0.5, 35.0), heights
     return (np.concatenate(parts) if parts else np.zeros((0, 3))), np.array(offsets, dtype=np.int64)
 
 
+def fit_plane(points, max_z=-0.5, dist_threshold=0.01, iterations=1000, seed=0):
+    """keyframe.py:417-436 calculate_plane (deterministic RANSAC convention, see icp_oracle.cpp).  Returns ([a,b,c,d], inliers)."""
+    p = _pts(points)
+    pl = np.zeros(4)
+    lib().orc_fit_plane.restype = ctypes.c_int
+    n_in = lib().orc_fit_plane(_d(p), len(p), ctypes.c_double(max_z), ctypes.c_double(dist_threshold), int(iterations),
+                               ctypes.c_ulonglong(int(seed)), _d(pl))
+    return pl, int(n_in)
+
+
+def segment_plane(points, plane_model, threshold=0.4):
+    """keyframe.py:438-461 (the reference's own numpy): indices of the points near the plane and of the others."""
+    points = np.asarray(points, dtype=np.float64)
+    a, b, c, d = [float(v) for v in plane_model]
+    dist = np.abs(a * points[:, 0] + b * points[:, 1] + c * points[:, 2] + d) / np.sqrt(a * a + b * b + c * c)
+    near = dist < threshold
+    return np.where(near)[0], np.where(~near)[0]
+
+
+def preprocess_two_planes(points_f32, plane_model=None, voxel_size=None, normal_radius=0.3, normal_radius_ground=0.5, max_nn=300, max_nn_gd=300,
+                          seed=0):
+    """keyframe.py:164-189 preprocess_icp2planes: filter -> [voxel] -> plane model -> split -> normals of both parts (radius
+    0.5 / max_nn_gd on the ground, 0.3 / max_nn elsewhere).  Returns (plane, (ground pts, normals), (other pts, normals))."""
+    p, _ = preprocess(points_f32, voxel_size=voxel_size, method="icppointpoint")
+    if plane_model is None:
+        plane_model, _ = fit_plane(p, seed=seed)
+    near, far = segment_plane(p, plane_model)
+    g, o = p[near], p[far]
+    return plane_model, (g, estimate_normals(g, normal_radius_ground, max_nn_gd)), (o, estimate_normals(o, normal_radius, max_nn))
+
+
 def preprocess(points_f32, voxel_size=None, method="icppointplane", min_radius=0.5, max_radius=35, min_height=-1.0,
                max_height=50.0, normal_radius=0.3, max_nn=300):
     """keyframe.py:148-162: filter → optional voxel → normals (point-plane only).  Input is the float32 PCD

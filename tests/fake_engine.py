@@ -48,6 +48,18 @@ class OracleEngine:
         pts, nrm, _ = self.pre[int(scan_id)]
         return (pts, nrm) if normals else pts
 
+    def fit_plane(self, scan_id, max_z=-0.5, dist_threshold=0.01, iterations=1000, seed=0):
+        self.calls.append(("fit_plane", int(scan_id)))
+        return orc.fit_plane(self.pre[int(scan_id)][0], max_z, dist_threshold, iterations, seed)
+
+    def split_plane(self, src_id, plane_model, threshold, near_id, far_id):
+        self.calls.append(("split_plane", int(src_id)))
+        pts = self.pre[int(src_id)][0]
+        near, far = orc.segment_plane(pts, plane_model, threshold)
+        self.upload(near_id, pts[near])
+        self.upload(far_id, pts[far])
+        return len(near), len(far)
+
     def map_build(self, scan_ids, transforms, p):
         self.calls.append(("map_build", len(scan_ids)))
         self.preprocess(scan_ids, p)

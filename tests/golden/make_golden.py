@@ -29,6 +29,14 @@ def install_stubs():
         def __init__(self, points=None):
             self.points = points
 
+        def select_by_index(self, index, invert=False):          # order-preserving, like Open3D's
+            pts = np.asarray(self.points)
+            if invert:
+                mask = np.ones(len(pts), dtype=bool)
+                mask[np.asarray(index, dtype=np.int64)] = False
+                return PointCloud(pts[mask])
+            return PointCloud(pts[np.asarray(index, dtype=np.int64)])
+
     o3d.geometry.PointCloud = PointCloud
     o3d.utility.Vector3dVector = lambda a: np.array(a, dtype=np.float64)
     sys.modules["open3d"] = o3d
@@ -101,6 +109,24 @@ def main():
     np.savez_compressed(os.path.join(OUT, "se3_helpers.npz"), mats=np.array(mats), invs=np.array(invs),
                         prods=np.array(prods), quats=np.array(quats), eulers=np.array(eulers), eulers2=np.array(eulers2),
                         gimbal_mats=np.array(gimbal_mats), gimbal_e1=np.array(gimbal_e1), gimbal_e2=np.array(gimbal_e2))
+    # 'icp2planes' pieces the reference implements itself: segment_plane (keyframe.py:438-461, own numpy) and the
+    # component merge of local_registration_two_planes (keyframe.py:282-292: t2v(n=3) of both results, tx ty gamma from
+    # the non-ground solution, tz alpha beta from the ground solution, HomogeneousMatrix(position, Euler))
+    from artelib.euler import Euler
+    cloud = rng.uniform(-30, 30, size=(3000, 3))
+    cloud[:, 2] = rng.uniform(-1.2, 3.0, size=3000)
+    plane = np.array([0.01, -0.02, 0.999, 0.69])
+    cloud[:40, 2] = (-(plane[0] * cloud[:40, 0] + plane[1] * cloud[:40, 1] + plane[3]) / plane[2]) + np.linspace(-0.41, 0.41, 40)
+    kf2 = KeyFrame(directory="", scan_time=0, voxel_size=None)
+    near_pc, far_pc = kf2.segment_plane(plane, pcd=PointCloud(cloud))
+    t2v3, merged = [], []
+    for k in range(32):
+        t2v3.append(HomogeneousMatrix(np.array(mats[k])).t2v(n=3))
+    for k in range(16):
+        t1, t2 = t2v3[k], t2v3[k + 16]
+        merged.append(HomogeneousMatrix(np.array([t2[0], t2[1], t1[2]]), Euler([t1[3], t1[4], t2[5]])).array)
+    np.savez_compressed(os.path.join(OUT, "two_planes.npz"), cloud=cloud, plane=plane, near=np.asarray(near_pc.points),
+                        far=np.asarray(far_pc.points), mats=np.array(mats), t2v3=np.array(t2v3), merged=np.array(merged))
     print("wrote", os.listdir(OUT))
 
 

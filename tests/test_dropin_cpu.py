@@ -133,3 +133,103 @@ def test_reference_scanmatcher_runs_unmodified_on_dropin(tmp_path):
         for k in list(sys.modules):
             if k not in saved_mods:
                 del sys.modules[k]
+
+
+def test_two_planes_pieces_match_reference_golden(golden_dir):
+    """'icp2planes' (SURVEY.md §8 f-2): the reference's own numpy split (keyframe.py:438-461) and component merge
+    (keyframe.py:282-292), generated by importing the reference (tests/golden/make_golden.py)."""
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, "two_planes.npz"))
+    near, far = orc.segment_plane(g["cloud"], g["plane"], 0.4)
+    np.testing.assert_array_equal(g["cloud"][near], g["near"])
+    np.testing.assert_array_equal(g["cloud"][far], g["far"])
+    assert 0 < len(near) < len(g["cloud"])
+    for T, t in zip(g["mats"], g["t2v3"]):
+        np.testing.assert_allclose(HomogeneousMatrix(T).t2v(n=3), t, rtol=0, atol=1e-12)
+    sys.path.insert(0, DROPIN)
+    saved = dict(sys.modules)
+    try:
+        for m in [k for k in sys.modules if k.split(".")[0] in ("config", "keyframemanager")]:
+            del sys.modules[m]
+        from keyframemanager.keyframe import merge_two_planes
+        for k in range(16):
+            M = merge_two_planes(g["mats"][k], g["mats"][k + 16])
+            np.testing.assert_allclose(M.array, g["merged"][k], rtol=0, atol=1e-12)
+    finally:
+        sys.path.remove(DROPIN)
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+
+
+def test_oracle_plane_fit_is_reproducible_and_sane():
+    from oracle import oracle as orc
+    seq = synth.Sequence(1, synth.SMALL_32, start=12.0)
+    p, _ = orc.preprocess(seq.scans[0], method="icppointpoint")
+    pl, n_in = orc.fit_plane(p, seed=0)
+    pl2, n2 = orc.fit_plane(p, seed=0)
+    np.testing.assert_array_equal(pl, pl2)
+    assert n_in == n2 > 0.5 * (p[:, 2] < -0.5).sum()
+    assert abs(np.linalg.norm(pl[:3]) - 1) < 1e-12 and abs(abs(pl[2]) - 1) < 1e-3 and abs(abs(pl[3]) - synth.SENSOR_HEIGHT) < 0.02
+    # inlier count of the returned model, recomputed with numpy
+    low = p[p[:, 2] < -0.5]
+    assert (np.abs(low @ pl[:3] + pl[3]) < 0.01).sum() == n_in
+    pl3, _ = orc.fit_plane(p, seed=1)
+    assert np.abs(pl3 - pl).max() < 0.02                 # another seed: another, equally good, hypothesis
+    # too few points below the height: no model
+    assert orc.fit_plane(p, max_z=-5.0)[1] == 0
+
+
+def test_dropin_icp2planes_on_oracle_engine(tmp_path):
+    """Host logic of the 'icp2planes' method: preprocess -> plane -> split -> two registrations in one batch -> merge."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_engine import OracleEngine
+    from oracle import oracle as orc
+    saved_path, saved_mods = list(sys.path), dict(sys.modules)
+    fake = OracleEngine()
+    runtime.set_engine(fake)
+    try:
+        for m in [k for k in sys.modules if k.split(".")[0] in ("config", "keyframemanager")]:
+            del sys.modules[m]
+        sys.path.insert(0, DROPIN)
+        import keyframemanager.keyframemanager as kfm
+        from keyframemanager.keyframe import merge_two_planes
+        seq = synth.Sequence(3, synth.TINY_16, start=30.0)
+        d = str(tmp_path / "euroc")
+        times = euroc_synth.write_euroc_tree(d, seq, method="icp2planes")
+        km = kfm.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icp2planes")
+        km.add_keyframes(keyframe_sampling=1)
+        km.load_pointclouds()
+        for i in range(3):
+            km.pre_process(i)
+        T01 = km.compute_transformation(0, 1, HomogeneousMatrix(seq.relative_odo(0, 1)))
+        assert [c for c in fake.calls if c[0] == "icp_batch"] == [("icp_batch", 2)]
+        pre = [orc.preprocess_two_planes(s) for s in seq.scans]
+        np.testing.assert_array_equal(km.keyframes[0].plane_model, pre[0][0])
+        np.testing.assert_array_equal(km.keyframes[0].pointcloud_ground_plane.points, pre[0][1][0])
+        np.testing.assert_array_equal(km.keyframes[0].pointcloud_non_ground_plane.points, pre[0][2][0])
+        init = seq.relative_odo(0, 1)
+        ra = orc.icp(pre[1][1][0], pre[0][1][0], pre[0][1][1], init, orc.P2PLANE)
+        rb = orc.icp(pre[1][2][0], pre[0][2][0], pre[0][2][1], init, orc.P2PLANE)
+        want = merge_two_planes(ra.transformation, rb.transformation).array
+        np.testing.assert_allclose(T01.array, want, rtol=0, atol=1e-12)
+        gt = seq.relative_gt(0, 1)
+        assert np.linalg.norm(T01.array[:3, 3] - gt[:3, 3]) < 0.05
+        # batched variant and a caller-supplied plane model
+        Ts, _ = km.compute_transformations([(0, 1), (1, 2)], [HomogeneousMatrix(seq.relative_odo(0, 1)), HomogeneousMatrix(seq.relative_odo(1, 2))])
+        np.testing.assert_array_equal(Ts[0].array, T01.array)
+        kf = kfm.KeyFrame(d, times[0], None)
+        kf.load_pointcloud()
+        kf.plane_model = np.array([0.0, 0.0, 1.0, 0.69])
+        kf.pre_process(method="icp2planes")
+        assert ("fit_plane", kf._scan_id) not in fake.calls
+        pw = orc.preprocess_two_planes(seq.scans[0], plane_model=[0.0, 0.0, 1.0, 0.69])
+        np.testing.assert_array_equal(kf.pointcloud_ground_plane.points, pw[1][0])
+        km.unload_pointcloud(0)
+        assert km.keyframes[0].pointcloud_ground_plane is None
+    finally:
+        runtime.set_engine(None)
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]

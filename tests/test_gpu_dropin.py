@@ -133,3 +133,33 @@ def test_loop_closing_triangle_one_device_batch(kfm_module, tmp_path):
         ref = orc.icp(pre[j][0], pre[i][0], pre[i][1], init, orc.P2PLANE)
         want = np.linalg.inv(T0_gps.array) @ ref.transformation @ T0_gps.array
         assert np.abs(T2 - want).max() < 1e-4
+
+
+def test_icp2planes_method(kfm_module, tmp_path):
+    """'icp2planes' through the drop-in (keyframe.py:164-189, 262-295): preprocess -> plane -> split -> two point-to-plane
+    registrations in one batch -> component merge, against the same pipeline on the oracle."""
+    from keyframemanager.keyframe import merge_two_planes
+    seq = synth.Sequence(3, synth.SMALL_32, start=30.0)
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq, method="icp2planes")
+    km = kfm_module.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icp2planes")
+    km.add_keyframes(keyframe_sampling=1)
+    km.load_pointclouds()
+    km.pre_process_many(range(3))
+    pre = [orc.preprocess_two_planes(s) for s in seq.scans]
+    for i in range(3):
+        np.testing.assert_array_equal(km.keyframes[i].plane_model, pre[i][0])
+        np.testing.assert_array_equal(km.keyframes[i].pointcloud_ground_plane.points, pre[i][1][0])
+        np.testing.assert_array_equal(km.keyframes[i].pointcloud_non_ground_plane.points, pre[i][2][0])
+    odo = [HomogeneousMatrix(seq.relative_odo(i, i + 1)) for i in range(2)]
+    single = [km.compute_transformation(i, i + 1, odo[i]) for i in range(2)]
+    batch, _ = km.compute_transformations([(0, 1), (1, 2)], odo)
+    for i in range(2):
+        np.testing.assert_array_equal(single[i].array, batch[i].array)
+        ra = orc.icp(pre[i + 1][1][0], pre[i][1][0], pre[i][1][1], odo[i].array, orc.P2PLANE)
+        rb = orc.icp(pre[i + 1][2][0], pre[i][2][0], pre[i][2][1], odo[i].array, orc.P2PLANE)
+        want = merge_two_planes(ra.transformation, rb.transformation).array
+        assert np.abs(single[i].array - want).max() < 1e-4
+        assert np.linalg.norm(single[i].array[:3, 3] - seq.relative_gt(i, i + 1)[:3, 3]) < 0.05
+    km.unload_pointcloud(0)
+    assert km.keyframes[0].pointcloud_ground_plane is None

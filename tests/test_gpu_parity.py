@@ -401,3 +401,37 @@ def test_map_build_bit_exact(eng, seq32, voxel):
     assert r["fitness"][0] > 0.9
     for k in ids + [7100, 7101]:
         eng.free(k)
+
+
+@pytest.mark.parametrize("voxel", [None, 0.25])
+def test_plane_fit_and_split_bit_exact(eng, seq32, voxel):
+    """SURVEY.md §8 f-2 pieces: reproducible RANSAC plane (keyframe.py:417-436) and the split by plane distance
+    (keyframe.py:438-461), against the oracle - same hash samples, same operation order, so bit-exact."""
+    eng.upload(7300, seq32.scans[0])
+    eng.preprocess([7300], eng.make_preprocess_params(voxel_size=voxel, want_normals=False))
+    pts = eng.get_points(7300)
+    for seed in (0, 5):
+        pl, n_in = eng.fit_plane(7300, -0.5, 0.01, 1000, seed)
+        wpl, wn = orc.fit_plane(pts, -0.5, 0.01, 1000, seed)
+        np.testing.assert_array_equal(pl, wpl)
+        assert n_in == wn > 100
+    n_near, n_far = eng.split_plane(7300, pl, 0.4, 7301, 7302)
+    near, far = orc.segment_plane(pts, pl, 0.4)
+    assert (n_near, n_far) == (len(near), len(far)) and n_near > 0 and n_far > 0
+    p = eng.make_preprocess_params(0.0, 35.0, -1.0, 50.0, want_normals=True, normal_radius=0.5)
+    p.min_radius2 = -1.0
+    eng.preprocess([7301, 7302], p)
+    g, gn = eng.get_points(7301, normals=True)
+    r = eng.get_points(7302)
+    np.testing.assert_array_equal(g, pts[near])
+    np.testing.assert_array_equal(r, pts[far])
+    on = orc.estimate_normals(pts[near], 0.5, 300)
+    err = np.minimum(np.linalg.norm(gn - on, axis=1), np.linalg.norm(gn + on, axis=1))
+    assert err.max() < 1e-6
+    # a plane far away from every point: everything lands in the second scan; no usable points -> error
+    assert eng.split_plane(7300, [0.0, 0.0, 1.0, -100.0], 0.4, 7301, 7302) == (0, len(pts))
+    assert eng.info(7302)["n_raw"] == len(pts) and eng.info(7301)["n_raw"] == 0
+    with pytest.raises(engine.EngineError):
+        eng.fit_plane(7300, -50.0, 0.01, 100, 0)
+    for k in (7300, 7301, 7302):
+        eng.free(k)
