@@ -325,13 +325,16 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
         // ---- pass B: accumulate the buckets below bstar, collect bucket bstar for exact ranking
         auto pass_b = [&](const int bstar) -> int {
             int ncand = 0;
+            // narrow records: the float32 histogram may have put a candidate one bucket off, so the k-th nearest lies in
+            // exact bucket bstar-1 .. bstar+1: everything below is taken whole, those three buckets are ranked exactly
+            const int blo = bstar == kBins ? kBins : (WIDE ? bstar : bstar - 1), bhi = WIDE ? bstar : bstar + 1;
             if constexpr (!WIDE) {
                 // float32 bucket coordinate u = d2f * buckets / r^2 (absolute error < 1e-3): two compares settle almost every
                 // candidate - certainly below bucket bstar (taken), certainly above it (dropped); the rest is decided exactly
                 int* ncand_s = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 16);
                 if (lane == 0) *ncand_s = 0;
                 __syncwarp();
-                const float u_lo = (float)min(bstar, kBins) - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bstar + 1) + 2e-3f;
+                const float u_lo = (float)blo - 2e-3f, u_hi = (float)(bstar == kBins ? kBins : bhi + 1) + 2e-3f;
                 auto take_one = [&](const CandEval<WIDE>& c, unsigned j) {
                     const float u = c.d2f * bsf;
                     if (u < u_lo) {
@@ -340,9 +343,9 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
                         const double d2 = c.exact(qx, qy, qz);
                         if (d2 < rq2) {
                             const int b = min(kBins - 1, (int)(d2 * bin_scale));
-                            if (b < bstar) {
+                            if (b < blo) {
                                 accumulate(c.x(), c.y(), c.z());
-                            } else if (b == bstar) {
+                            } else if (b <= bhi) {
                                 const int slot = atomicAdd(ncand_s, 1);
                                 if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
                             }
@@ -409,13 +412,11 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             __syncwarp();
             auto count_one = [&](const CandEval<WIDE>& c) {
                 if constexpr (!WIDE) {
-                    // float32 bucket coordinate: beyond the last bucket -> outside the radius; safely inside a bucket
-                    // -> count it; within 2e-3 of an edge (or in the last bucket) -> decide exactly
+                    // float32 bucket coordinate (error < 1e-3 buckets): membership in the radius is decided exactly, the
+                    // bucket itself may be off by one - the selection allows for that (the boundary is three buckets wide)
                     const float u = c.d2f * bsf;
-                    if (u > (float)kBins + 2e-3f) return;
-                    const int b = (int)u;
-                    const float fr = u - (float)b;
-                    if (fr > 2e-3f && fr < 1.0f - 2e-3f && b < kBins - 1) { atomicAdd(&hist[b], 1); return; }
+                    if (u < (float)kBins - 2e-3f) { atomicAdd(&hist[(int)u], 1); return; }      // certainly inside the radius
+                    if (u > (float)kBins + 2e-3f) return;                                        // certainly outside
                     const double d2 = c.exact(qx, qy, qz);
                     if (d2 < rq2) atomicAdd(&hist[min(kBins - 1, (int)(d2 * bin_scale))], 1);
                 } else {
@@ -470,6 +471,8 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
         const int ncand = pass_b(bstar);
         if (bstar != kBins) {
             __syncwarp();
+            const int blo = WIDE ? bstar : bstar - 1, bhi = WIDE ? bstar : bstar + 1;
+            need = np.max_nn - warp_sum(cnt);          // still missing once the buckets below the boundary are taken whole
             if (ncand <= kCand) {
                 // exact rank inside the boundary bucket; the `need` smallest (d2, index) keys join the neighbourhood
                 double td2 = 0;
@@ -506,7 +509,8 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
                             int idx;
                             load_rec(recs + u, x, y, z, idx);
                             const double d2 = sqdist(qx, qy, qz, x, y, z);
-                            if (d2 < rq2 && min(kBins - 1, (int)(d2 * bin_scale)) == bstar && key_less(last_d2, last_idx, d2, idx) &&
+                            const int bb = min(kBins - 1, (int)(d2 * bin_scale));
+                            if (d2 < rq2 && bb >= blo && bb <= bhi && key_less(last_d2, last_idx, d2, idx) &&
                                 key_less(d2, idx, md2, midx)) { md2 = d2; midx = idx; }
                         }
                     }
