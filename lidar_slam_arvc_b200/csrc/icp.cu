@@ -50,12 +50,15 @@ __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int 
 
 // float32 screening threshold for a best-so-far d2 (see DESIGN.md "float32 screening"): narrow target records are
 // exact float32 values, so |d2f - d2| <= 2e-6 d2 + 3.5 sqrt(d2) e + 3 e^2 with e the rounding of the query coordinates.
-// sqrt(b) is bounded from above with one MUFU: b * rsqrt(b) (2 ulp) inflated by 1e-6, + 1e-15 for b below the clamp.
-__device__ __forceinline__ float screen_thr(double best_d2, float e) {
-    const float b = __double2float_ru(best_d2);
-    const float s = b * rsqrtf(fmaxf(b, 1e-30f)) * (1.0f + 1e-6f) + 1e-15f;
-    return (b * (1.0f + 4e-6f) + 3.6f * e * s + 3.1f * e * e) * (1.0f + 1e-6f);
-}
+// The threshold is re-evaluated under divergence every time a lane's best improves, so it is kept to one conversion and
+// one FMA: sqrt(b) <= 5 b + 0.05 (AM-GM around 0.1 m, the typical match distance) turns the bound into k1 * b + k0.
+// The slack this adds is ~1e-7 m^2 - it only lets a few more candidates through to the exact float64 comparison.
+struct ScreenThr {
+    float k0, k1;
+    __device__ __forceinline__ explicit ScreenThr(float e)
+        : k0((0.18f * e + 3.1f * e * e) * (1.0f + 1e-6f)), k1((1.0f + 4e-6f + 18.0f * e) * (1.0f + 1e-6f)) {}
+    __device__ __forceinline__ float operator()(double best_d2) const { return fmaf(__double2float_ru(best_d2), k1, k0); }
+};
 
 template <bool TW>
 __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, int level,
@@ -70,7 +73,8 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
     const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
     const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
     double gbest = in_d2;                       // group-wide best d2 (every lane holds the same value)
-    float thr = screen_thr(gbest, e);
+    const ScreenThr screen_thr(e);
+    float thr = screen_thr(gbest);
     lb.d2 = in_d2; lb.idx = in_idx; lb.pos = -1;
 
     for (int l = level; l <= g.top_level; ++l) {
@@ -137,7 +141,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                             if (d2f <= thr) {
                                 const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
                                 const int idx = __float_as_int(v.w);
-                                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); thr = screen_thr(d2, e); }
+                                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); thr = screen_thr(d2); }
                             }
                         }
                     }
@@ -156,7 +160,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                 double m = lb.d2;
 #pragma unroll
                 for (int o = kG / 2; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(gmask, m, o, kG));
-                if (m < gbest) { gbest = m; thr = fminf(thr, screen_thr(m, e)); }
+                if (m < gbest) { gbest = m; thr = fminf(thr, screen_thr(m)); }
             } else {
                 // expand into the eight children, lane r <-> r-th nearest octant
                 const int cx = (int)(en4.z & 1023u), cy = (int)((en4.z >> 10) & 1023u), cz = (int)(en4.z >> 20);
@@ -482,7 +486,8 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
         unsigned* rcell = reinterpret_cast<unsigned*>(runs + kUnionMax);   // ... + their cell offsets (4 B)
         const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
         const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
-        float thr = screen_thr(b.d2, e);
+        const ScreenThr screen_thr(e);
+        float thr = screen_thr(b.d2);
         const int gshift = lane & ~(kG - 1);
         // step -1 (queries without any bound, i.e. the cold pass): look only into the finest cell holding the query; whatever
         // is found there bounds the real search, whose ball then touches a few cells instead of the full 3x3x3 block
@@ -551,7 +556,8 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                     const int kz0 = (cell_coord(qz - qr, g.oz, g.inv_c0) >> lu) - z0, kz1 = (cell_coord(qz + qr, g.oz, g.inv_c0) >> lu) - z0;
                     const float qxf = (float)qx, qyf = (float)qy, qzf = (float)qz;
                     const float qe = (float)(fmax(fabs(qx), fmax(fabs(qy), fabs(qz))) * 6.0e-8 + 1e-30);
-                    float qthr = screen_thr(lb.d2, qe), g1 = INFINITY, g2 = INFINITY;
+                    const ScreenThr qscreen(qe);
+                    float qthr = qscreen(lb.d2), g1 = INFINITY, g2 = INFINITY;
                     for (int rr = 0; rr < nr; ++rr) {
                         const unsigned rc = rcell[rr];
                         const int ox = (int)(rc & 255u), oy = (int)((rc >> 8) & 255u), oz = (int)(rc >> 16);
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                                 if (d2f <= qthr) {
                                     const double d2 = sqdist(qx, qy, qz, (double)v.x, (double)v.y, (double)v.z);
                                     const int idx = __float_as_int(v.w);
-                                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); qthr = screen_thr(d2, qe); }
+                                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); qthr = qscreen(d2); }
                                 }
                             }
                         }
@@ -605,9 +611,15 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                     while (rr < nr && fill < kStage) {
                         const uint2 run = runs[rr];
                         const unsigned len = min(run.y - run.x - off, (unsigned)(kStage - fill));
-                        for (unsigned q = gl; q < len; q += kG) {
-                            stage[fill + q] = __ldg(reinterpret_cast<const float4*>(trecs + run.x + off + q));
+                        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(trecs + run.x + off);
+                        for (unsigned q = gl; q < len; q += 2 * kG) {      // two loads in flight per lane
+                            const bool two = q + kG < len;
+                            const float4 v0 = __ldg(src4 + q);
+                            float4 v1 = v0;
+                            if (two) v1 = __ldg(src4 + q + kG);
+                            stage[fill + q] = v0;
                             spos[fill + q] = (int)(run.x + off + q);
+                            if (two) { stage[fill + q + kG] = v1; spos[fill + q + kG] = (int)(run.x + off + q + kG); }
                         }
                         fill += (int)len;
                         off += len;
@@ -624,7 +636,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
                         if (want && d2f <= thr) {
                             const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
                             const int idx = __float_as_int(v.w);
-                            if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = spos[j]; thr = screen_thr(d2, e); }
+                            if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = spos[j]; thr = screen_thr(d2); }
                         }
                     }
                     __syncwarp(gmask);
