@@ -68,11 +68,20 @@ def full(path):
     print("# dram traffic per launch (bytes):", json.dumps(traffic))
 
 
-def traffic(path, n_scans=9):
-    """profiles/traffic.json from a --set full capture of tools/prof_target.py <n_scans> (k_normals + k_icp_search passes)."""
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units = rows[0], rows[1]
+def traffic(paths, n_scans=9):
+    """profiles/traffic.json from --set full captures of tools/prof_target.py <n_scans> (k_normals + k_icp_search passes);
+    several reports (comma separated) are merged."""
+    rows, hdr, units = [None, None], None, None
+    for path in paths.split(","):
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(out.splitlines()))
+        if hdr is None:
+            hdr, units = rr[0], rr[1]
+            rows += rr[2:]
+        else:                                   # same metric set: align the columns by name
+            pos = {h: i for i, h in enumerate(rr[0])}
+            rows += [[r[pos[h]] if h in pos else "0" for h in hdr] for r in rr[2:]]
+    path = paths
     idx = {h: i for i, h in enumerate(hdr)}
 
     def num(r, k):
