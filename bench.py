@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=99, help="keyframe pairs per GPU per step (BASELINE.md config 2: the 99 pairs of a 100-scan sequence)")
-    ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-pairs", type=int, default=6, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs of the cpu_baseline sample (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-voxel", action="store_true", help="skip the extra voxel_size 0.2 measurement")
