@@ -752,11 +752,14 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restri
     const double* T = st->T;
     const double T0 = T[0], T1 = T[1], T2 = T[2], T3 = T[3], T4 = T[4], T5 = T[5], T6 = T[6], T7 = T[7], T8 = T[8], T9 = T[9],
                  T10 = T[10], T11 = T[11];
-#pragma unroll 1
+    int posv[kAccPts];                   // the matches of all the lane's points first: one exposed latency instead of four
+#pragma unroll
+    for (int j = 0; j < kAccPts; ++j) posv[j] = base + j * 32 < n ? pr.prev[base + j * 32] : -1;
+#pragma unroll
     for (int j = 0; j < kAccPts; ++j) {
         const int i = base + j * 32;
         if (i >= n) break;
-        const int pos = pr.prev[i];
+        const int pos = posv[j];
         int sidx = 0;
         if (pos < 0 && !pr.corr_trace) continue;
         double px, py, pz;
