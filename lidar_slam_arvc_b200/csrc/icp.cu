@@ -755,27 +755,39 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restri
     int posv[kAccPts];                   // the matches of all the lane's points first: one exposed latency instead of four
 #pragma unroll
     for (int j = 0; j < kAccPts; ++j) posv[j] = base + j * 32 < n ? pr.prev[base + j * 32] : -1;
+    // all gathers of the lane's points are issued before the arithmetic (clamped indices, results of invalid points unused)
+    double pxv[kAccPts], pyv[kAccPts], pzv[kAccPts], txv[kAccPts], tyv[kAccPts], tzv[kAccPts];
+    int sidxv[kAccPts], tidxv[kAccPts];
+    double4 nvv[kAccPts];
+#pragma unroll
+    for (int j = 0; j < kAccPts; ++j) {
+        const int i = min(base + j * 32, max(n - 1, 0));
+        const int pos = max(posv[j], 0);
+        load_rec(reinterpret_cast<const SRec*>(src.recs) + i, pxv[j], pyv[j], pzv[j], sidxv[j]);
+        load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pos, txv[j], tyv[j], tzv[j], tidxv[j]);
+        if (METHOD == 1) nvv[j] = reinterpret_cast<const double4*>(tgt.normals)[pos];
+    }
 #pragma unroll
     for (int j = 0; j < kAccPts; ++j) {
         const int i = base + j * 32;
         if (i >= n) break;
         const int pos = posv[j];
-        int sidx = 0;
-        if (pos < 0 && !pr.corr_trace) continue;
-        double px, py, pz;
-        load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
-        if (pos < 0) { pr.corr_trace[(size_t)pass * src.cap + sidx] = -1; continue; }
+        const int sidx = sidxv[j];
+        if (pos < 0) {
+            if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = -1;
+            continue;
+        }
+        const double px = pxv[j], py = pyv[j], pz = pzv[j];
         const double sx = T0 * px + T1 * py + T2 * pz + T3;
         const double sy = T4 * px + T5 * py + T6 * pz + T7;
         const double sz = T8 * px + T9 * py + T10 * pz + T11;
-        double tx, ty, tz;
-        int tidx;
-        load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pos, tx, ty, tz, tidx);
+        const double tx = txv[j], ty = tyv[j], tz = tzv[j];
+        const int tidx = tidxv[j];
         acc[27] += sqdist(sx, sy, sz, tx, ty, tz);
         acc[28] += 1.0;
         if (pr.corr_trace) pr.corr_trace[(size_t)pass * src.cap + sidx] = tidx;
         if (METHOD == 1) {
-            const double4 nv = reinterpret_cast<const double4*>(tgt.normals)[pos];
+            const double4 nv = nvv[j];
             const double r = (sx - tx) * nv.x + (sy - ty) * nv.y + (sz - tz) * nv.z;
             const double J[6] = {sy * nv.z - sz * nv.y, sz * nv.x - sx * nv.z, sx * nv.y - sy * nv.x, nv.x, nv.y, nv.z};
             int t = 0;
