@@ -55,7 +55,9 @@ int arvc_profile_report(arvc_ctx* ctx, char* buf, size_t cap);
 /* --- scans -----------------------------------------------------------------------------------------
  * Replaces KeyFrame.load_pointcloud's result handed to Open3D (keyframemanager/keyframe.py:41-45): the
  * PCD payload (float32 xyz, n points, NaNs allowed) is copied to the device.  Re-uploading an id replaces it.
- * The _f64 variant is for PCD files with double fields.  Asynchronous w.r.t. the host when `xyz` is pinned. */
+ * The _f64 variant is for PCD files with double fields.  Asynchronous w.r.t. the host when `xyz` is pinned (keep the
+ * buffer alive until arvc_sync): the copy runs on a dedicated copy stream and overlaps the kernels of scans uploaded
+ * earlier; arvc_scan_preprocess waits for it on the device. */
 int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n);
 int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n);
 /* Forget the cached preprocessing of a scan (host-side flag only).  The reference never sets

@@ -25,6 +25,8 @@ struct Scan {
     int n_raw = 0;
     bool f64 = false;
     void* d_raw = nullptr;
+    cudaEvent_t up_ev = nullptr;   // recorded on the copy stream after the upload; the compute stream waits for it once
+    bool up_pending = false;
     // persistent slab
     void* slab = nullptr;
     size_t slab_bytes = 0;
@@ -62,6 +64,7 @@ struct SlabPlanner {   // two-pass bump allocator: plan sizes, then hand out poi
 struct arvc_ctx {
     int device = 0;
     Launcher L;
+    cudaStream_t copy_stream = nullptr;   // host -> device uploads, so that they overlap the kernels of earlier scans
     std::string error;
     std::unordered_map<int64_t, std::unique_ptr<Scan>> scans;
     std::map<uint64_t, PendingBatch> pending;
@@ -137,8 +140,16 @@ struct arvc_ctx {
 
 namespace {
 
+// the compute stream may touch (or free) the raw cloud only after its upload on the copy stream has finished
+void await_upload(arvc_ctx* ctx, Scan* s) {
+    if (s->up_pending) cudaStreamWaitEvent(ctx->L.stream, s->up_ev, 0);
+    s->up_pending = false;
+}
+
 void release_scan(arvc_ctx* ctx, Scan* s) {
     cudaStream_t st = ctx->L.stream;
+    await_upload(ctx, s);
+    if (s->up_ev) { cudaEventDestroy(s->up_ev); s->up_ev = nullptr; }
     if (s->d_raw) cudaFreeAsync(s->d_raw, st);
     if (s->slab) cudaFreeAsync(s->slab, st);
     if (s->d_dev) cudaFreeAsync(s->d_dev, st);
@@ -170,8 +181,11 @@ int upload(arvc_ctx* ctx, int64_t id, const void* xyz, int n, bool f64) {
     s->id = id; s->n_raw = n; s->f64 = f64;
     const size_t bytes = (size_t)n * 3 * (f64 ? sizeof(double) : sizeof(float));
     if (n > 0) {
-        CK(cudaMallocAsync(&s->d_raw, bytes, ctx->L.stream));
-        CK(cudaMemcpyAsync(s->d_raw, xyz, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+        CK(cudaMallocAsync(&s->d_raw, bytes, ctx->copy_stream));
+        CK(cudaMemcpyAsync(s->d_raw, xyz, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventCreateWithFlags(&s->up_ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(s->up_ev, ctx->copy_stream));
+        s->up_pending = true;
     }
     ctx->scans[id] = std::move(s);
     return ARVC_OK;
@@ -241,7 +255,8 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ARVC_E_CUDA; }
     auto ctx = new arvc_ctx();
     ctx->device = device;
-    e = cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ARVC_E_CUDA; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -262,7 +277,9 @@ void arvc_ctx_destroy(arvc_ctx* ctx) {
     }
     for (auto& pf : ctx->pinned_free) cudaFreeHost(pf.second);
     for (auto& kv : ctx->scans) release_scan(ctx, kv.second.get());
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->L.stream);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->L.stream);
     delete ctx;
 }
@@ -271,6 +288,7 @@ const char* arvc_last_error(const arvc_ctx* ctx) { return ctx ? ctx->error.c_str
 
 int arvc_sync(arvc_ctx* ctx) {
     if (!ctx) return ARVC_E_ARG;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->L.stream));
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     return ARVC_OK;
@@ -387,6 +405,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         todo.push_back(s);
     }
     if (todo.empty()) return ARVC_OK;
+    for (Scan* s : todo) await_upload(ctx, s);
 
     // ---- allocate: persistent slab per scan, one scratch slab for the batch
     int cap_max = 0;
