@@ -119,7 +119,10 @@ constexpr int kCanon = 320;          // most neighbours the canonical (sorted, s
 //   canonical : double key_d2[kCanon] | int key_idx[kCanon] | int key_pos[kCanon] | int order[kCanon]
 constexpr int kScratch = kCanon * 20;  // bytes of the two overlapping layouts above
 constexpr int kTryRuns = 160;          // cells of the trial ball (6^3 = 216 before box pruning)
-constexpr int kWarpSmem = kScratch + (64 + kTryRuns) * 8;   // + cell runs, which outlive both layouts
+constexpr int kScratchSel = (kBins * 4 + kCand * 16 + 16 + 255) / 256 * 256;   // mode 0 never uses the canonical layout
+constexpr int kRunBytes = (64 + kTryRuns) * 8;              // cell runs, which outlive both layouts
+constexpr int kWarpSmem = kScratch + kRunBytes;             // mode 1
+constexpr int kWarpSmemSel = kScratchSel + kRunBytes;       // mode 0: 5.9 KB per warp instead of 8 KB leaves more L1
 constexpr int kSpecFactor3 = 7;        // up to kSpecFactor3/3 * max_nn candidates: speculative single pass at the full radius
 constexpr int kDenseFactor2 = 3;       // neighbourhoods with more than kDenseFactor2/2 * max_nn candidates try a smaller radius first
 static_assert(kBins * 4 + kCand * 16 + 16 <= kScratch, "selection layout must fit");
@@ -202,12 +205,12 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
     const int ncell = nx * ny * nz;            // <= 27 (64 when the inflated ball grazes a fourth cell): cell edge >= radius
 
-    unsigned char* wmem = s_raw + (size_t)w * kWarpSmem;
+    unsigned char* wmem = s_raw + (size_t)w * (mode == 0 ? kWarpSmemSel : kWarpSmem);
     int* hist = reinterpret_cast<int*>(wmem);
     double* cand_d2 = reinterpret_cast<double*>(wmem + kBins * 4);
     int* cand_idx = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 8);
     int* cand_pos = reinterpret_cast<int*>(wmem + kBins * 4 + kCand * 12);
-    uint2* runs_full = reinterpret_cast<uint2*>(wmem + kScratch);           // <= 64 runs: cells of the full radius
+    uint2* runs_full = reinterpret_cast<uint2*>(wmem + (mode == 0 ? kScratchSel : kScratch));   // <= 64 runs: cells of the full radius
     uint2* runs_try = runs_full + 64;                                       // <= kTryRuns runs: finer cells of the trial radius
 
     // ---- cells of the full radius (<= 27 at the level whose edge >= radius): lane c owns cell c
@@ -671,15 +674,15 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     np.bin_scale_f = (float)np.bin_scale;
     np.debug = getenv("ARVC_DEBUG_NORMALS") ? atoi(getenv("ARVC_DEBUG_NORMALS")) : 0;
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
-    const size_t smem = (size_t)kNrmWarps * kWarpSmem;
+    const size_t smem = (size_t)kNrmWarps * kWarpSmem, smem_sel = (size_t)kNrmWarps * kWarpSmemSel;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_normals<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem, d_scans, np, 0);
-    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem, d_scans, np, 0);
+    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
+    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem_sel, d_scans, np, 0);
     L.launch("normals_eigen", k_normals_eigen, dim3((cap_max + 127) / 128, n_scans), dim3(128), d_scans);
     // ill-conditioned points (a few per cent): the grid is sized for the worst case, blocks past the list length exit
     if (any_narrow) L.launch_smem("normals_redo", k_normals<false>, grid, block, smem, d_scans, np, 1);
