@@ -143,6 +143,7 @@ class KeyFrame():
     def _preprocess(self, params):
         self._require_loaded()
         runtime.get_engine().preprocess([self._scan_id], params)
+        self._last_params = params
         self._preprocessed_on_device = True
         self._filtered_cache = None
 
@@ -287,5 +288,10 @@ class KeyFrame():
 
     # ------------------------------------------------------------------ used by the map-building / viewer callers
     def transform(self, T):
-        pc = self.pointcloud_filtered
-        return PointCloud(np.array(pc.points), None if pc.normals is None else np.array(pc.normals)).transform(T)
+        """keyframe.py:399-400: the filtered cloud moved by T (Open3D PointCloud::Transform), computed on the device by the
+        map-building kernel; the keyframe's own cloud stays in the sensor frame (Open3D transforms in place)."""
+        params = getattr(self, "_last_params", None)
+        if not self._preprocessed_on_device or params is None:
+            raise RuntimeError("filter_radius_height() / pre_process() first")
+        xyz, _ = runtime.get_engine().map_build([self._scan_id], np.asarray(T, dtype=np.float64)[None], params)
+        return PointCloud(xyz)

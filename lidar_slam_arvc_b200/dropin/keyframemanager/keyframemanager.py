@@ -83,6 +83,7 @@ class KeyFrameManager():
         for kf in kfs:
             kf._preprocessed_on_device = True
             kf._filtered_cache = None
+            kf._last_params = kfs[0]._params(self.method == 'icppointplane')
 
     def compute_transformations(self, pairs, Tijs):
         """[(i, j), ...] and initial guesses -> list of iTj, one device batch.  Each keyframe's `last_result`-style record
@@ -130,9 +131,11 @@ class KeyFrameManager():
         for kf in kfs:
             kf._require_loaded()
         T = np.array([np.asarray(sampled[i].array, dtype=np.float64) for i in range(len(kfs))])
-        xyz, offsets = runtime.get_engine().map_build([kf._scan_id for kf in kfs], T, kfs[0]._params(False, radii, heights))
+        params = kfs[0]._params(False, radii, heights)
+        xyz, offsets = runtime.get_engine().map_build([kf._scan_id for kf in kfs], T, params)
         for kf in kfs:
             kf._filter_bounds = (radii, heights)
+            kf._last_params = params
             kf._preprocessed_on_device = True
             kf._filtered_cache = None
         self.map_offsets = offsets

@@ -57,6 +57,10 @@ def test_scanmatcher_loop(kfm_module, tmp_path, method, voxel):
     # the host view of the last keyframe matches the oracle's cloud (reference point order)
     pc = km.keyframes[-1].pointcloud_filtered
     np.testing.assert_array_equal(pc.points, pre[-1][0])
+    # KeyFrame.transform (keyframe.py:399-400) runs on the device and leaves the keyframe's own cloud in the sensor frame
+    moved = km.keyframes[-1].transform(seq.poses[-1])
+    np.testing.assert_array_equal(moved.points, orc.transform_points(pre[-1][0], seq.poses[-1]))
+    np.testing.assert_array_equal(km.keyframes[-1].pointcloud_filtered.points, pre[-1][0])
 
 
 def test_batched_loop_closing_equals_sequential(kfm_module, tmp_path):

@@ -79,6 +79,10 @@ def test_dropin_build_map_is_one_batch(tmp_path):
             if voxel is not None:
                 p, _, _ = orc.voxel_down_sample(p, voxel)
             np.testing.assert_array_equal(kf.pointcloud_filtered.points, p)
+            # KeyFrame.transform (keyframe.py:399-400): the filtered cloud in the global frame, keyframe itself untouched
+            moved = kf.transform(seq.poses[2])
+            np.testing.assert_array_equal(moved.points, orc.transform_points(p, seq.poses[2]))
+            np.testing.assert_array_equal(kf.pointcloud_filtered.points, p)
     finally:
         runtime.set_engine(None)
         sys.path[:] = saved_path
