@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--ref-pairs", type=int, default=6, help="pairs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-pairs", type=int, default=6, help="pairs of the cpu_baseline sample (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rank-stride", type=float, default=0.0,
+                    help="metres between the trajectory starts of consecutive ranks; 0 = the same synthetic sequence on every "
+                         "rank, i.e. exactly equal per-GPU work (weak scaling); > 0 gives every rank its own scans")
     ap.add_argument("--no-voxel", action="store_true", help="skip the extra voxel_size 0.2 measurement")
     return ap.parse_args()
 
@@ -49,7 +52,9 @@ def workload_config(pairs, n_gpus):
             "pairs_per_gpu_per_step": pairs, "scans_per_gpu_per_step": pairs + 1, "method": "icppointplane", "voxel_size": None,
             "max_corr_dist": 10.0, "criteria": "rel_fitness=1e-6 rel_rmse=1e-6 max_iter=30", "normals": "radius=0.3 max_nn=300",
             "l2": "inputs larger than L2 (every step re-streams %d MB of scans, grids and normals per GPU)" % (12 * (pairs + 1)),
-            "parallelism": "pairs sharded x%d, all-gather of 160 B records" % n_gpus}
+            "parallelism": "pairs sharded x%d, all-gather of 160 B records" % n_gpus,
+            "per_rank_data": "every rank processes its own copy of the same synthetic sequence (equal per-GPU work); "
+                             "--rank-stride > 0 gives every rank different scans"}
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -184,7 +189,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs
-    seq = synth.Sequence(P + 1, synth.OS1_64, start=30.0 + 11.0 * rank, workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
+    seq = synth.Sequence(P + 1, synth.OS1_64, start=30.0 + args.rank_stride * rank, workers=max(1, (os.cpu_count() or 1) // max(world, 1)))
     ids = np.arange(P + 1, dtype=np.int64)
     tg, sr = ids[:-1], ids[1:]
     init = np.array([seq.relative_odo(int(a), int(b)) for a, b in zip(tg, sr)])
@@ -208,21 +213,25 @@ def main():
         eng.invalidate(ids)
         eng.preprocess(ids, pp)
         rec = eng.icp_batch(tg, sr, init, ip)
-        return sharding.gather_records(rec, device=dev) if world > 1 else rec
+        return sharding.gather_records(rec, device=dev, counts=[P] * world) if world > 1 else rec
 
-    head = max(1, min(len(ids) // 8, 12))      # e2e: a small first chunk starts computing while the rest is still in flight
+    # e2e: geometrically growing chunks (6, 12, 24, ... scans) - the upload of chunk c+1 runs on the engine's copy stream
+    # while chunk c is preprocessed, also when several ranks share the host's PCIe / memory bandwidth
+    bounds, head = [0], 6
+    while bounds[-1] < len(ids):
+        bounds.append(min(len(ids), bounds[-1] + head * 2 ** (len(bounds) - 1)))
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] < head:
+        bounds.pop(-2)
 
     def e2e_path():
-        """Host scans -> records: uploads run on the engine's copy stream, so the preprocessing of the first chunk
-        overlaps the upload of the others; the ICP batch is the same single call."""
-        for k in range(head):
-            eng.upload_ptr(k, pinned[k].data_ptr(), pinned[k].shape[0])
-        eng.preprocess(ids[:head], pp)
-        for k in range(head, len(pinned)):
-            eng.upload_ptr(k, pinned[k].data_ptr(), pinned[k].shape[0])
-        eng.preprocess(ids[head:], pp)
+        """Host scans -> records: every chunk is uploaded (copy stream) and then preprocessed (compute stream, waits for
+        its own uploads only); the ICP batch is the same single call."""
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            for k in range(lo, hi):
+                eng.upload_ptr(k, pinned[k].data_ptr(), pinned[k].shape[0])
+            eng.preprocess(ids[lo:hi], pp)
         rec = eng.icp_batch(tg, sr, init, ip)
-        return sharding.gather_records(rec, device=dev) if world > 1 else rec
+        return sharding.gather_records(rec, device=dev, counts=[P] * world) if world > 1 else rec
 
     def barrier():
         eng.sync()
@@ -257,6 +266,8 @@ def main():
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    if os.environ.get("ARVC_BENCH_RANK_LOG"):
+        print("[rank %d] device %.2f ms for %d steps, host step ms %s" % (rank, dev_ms, args.steps, step_ms), file=sys.stderr, flush=True)
     launches = eng.kernel_launches() - l0
     prof_raw = eng.profile_report()
     prof, icp_passes = {}, {}
@@ -339,7 +350,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk, "step_ms": step_ms, "e2e_step_ms": e2e_step_ms, "roofline": roofline,
             "mean_icp_updates": float(np.mean(own["updates"])), "icp_updates": [int(u) for u in own["updates"]], "points_per_scan": int(n_pts.mean()),
             "notes": {"value_region": "carries one CUDA-event pair per kernel launch (the per-kernel times of `roofline`), ~1 % overhead",
-                      "e2e_region": "uploads on the engine's copy stream: the first %d scans are preprocessed while the others are in flight" % head}}
+                      "e2e_region": "uploads on the engine's copy stream in chunks of %s scans: chunk c is preprocessed while chunk c+1 is in flight" % [b - a for a, b in zip(bounds[:-1], bounds[1:])]}}
 
     # ---- extra (BASELINE.md config 2 is reported for voxel_size None and 0.2): same batch with voxel down-sampling on
     if world == 1 and not args.no_voxel:

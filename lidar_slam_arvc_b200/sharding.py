@@ -30,9 +30,10 @@ def sort_pairs_for_cache(tgt_ids, src_ids):
     return np.lexsort((s, t))
 
 
-def gather_records(records, device=None, group=None):
+def gather_records(records, device=None, group=None, counts=None):
     """All-gather per-rank result records (numpy RESULT_DTYPE, possibly different counts per rank); every rank
-    returns the concatenation in rank order.  Without an initialised process group: identity."""
+    returns the concatenation in rank order.  Without an initialised process group: identity.
+    `counts` (records per rank, e.g. from shard_bounds) saves the exchange of the counts: one collective per batch."""
     import torch
     import torch.distributed as dist
     records = np.ascontiguousarray(records, dtype=RESULT_DTYPE)
@@ -40,10 +41,14 @@ def gather_records(records, device=None, group=None):
         return records
     world = dist.get_world_size(group)
     dev = torch.device(device) if device is not None else torch.device("cpu")
-    n = torch.tensor([len(records)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    if counts is None:
+        n = torch.tensor([len(records)], dtype=torch.int64, device=dev)
+        all_n = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_n, n, group=group)
+        counts = [int(c) for c in all_n.cpu().tolist()]
+    elif len(counts) != world or int(counts[dist.get_rank(group)]) != len(records):
+        raise ValueError("gather_records: counts do not match this rank's records")
+    counts = [int(c) for c in counts]
     cap = max(max(counts), 1)
     words = RESULT_DTYPE.itemsize // 8
     buf = torch.zeros((cap, words), dtype=torch.float64, device=dev)

@@ -45,6 +45,13 @@ def _worker(rank, world, port, counts, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         out = sharding.gather_records(_make_records(rank, counts[rank]))
+        known = sharding.gather_records(_make_records(rank, counts[rank]), counts=list(counts))     # counts known: one collective
+        assert known.tobytes() == out.tobytes()
+        try:
+            sharding.gather_records(_make_records(rank, counts[rank]), counts=[c + 1 for c in counts])
+            raise AssertionError("wrong counts accepted")
+        except ValueError:
+            pass
         q.put((rank, out.tobytes()))
     finally:
         dist.destroy_process_group()
