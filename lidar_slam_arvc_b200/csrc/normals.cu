@@ -174,19 +174,9 @@ template <> struct CandEval<true> {
 // mode 1: only the points k_normals_eigen flagged as ill-conditioned: same search, then the canonical re-summation
 //         and the solve inside the warp.
 template <bool WIDE>
-__global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
+__device__ __forceinline__ void normals_point(const ScanDev& s, const NormalParams& np, const int mode, const int p, unsigned char* s_raw) {
     typedef typename RecT<WIDE>::type Rec;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const ScanDev& s = scans[blockIdx.y];
-    if ((s.wide != 0) != WIDE) return;
-    const int n = s.counts[CNT_NPTS];
     const int w = threadIdx.x >> 5, lane = lane_id();
-    int p = blockIdx.x * kNrmWarps + w;
-    if (mode == 1) {
-        if (p >= s.counts[CNT_NREDO]) return;
-        p = s.redo_list[p];
-    }
-    if (p >= n) return;
     const Rec* __restrict__ recs = reinterpret_cast<const Rec*>(s.recs);
     double qx, qy, qz;
     int qidx;
@@ -562,7 +552,9 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
     }
     V3 nv{0.0, 0.0, 1.0};
     int redo = 0;
-    if (lane == 0) {
+    // mode 1 only gets here: k_normals_eigen has already found the eigen-gap of this point below kIllGap (with cnt <= kCanon)
+    redo = (cnt >= 3 && cnt <= kCanon) ? 1 : 0;
+    if (!redo && lane == 0) {
         double gap = 1.0;
         if (cnt >= 3) {
             // centred second moments: better conditioned than raw cumulants, equal to them up to rounding
@@ -570,12 +562,10 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             const double mx = sx * inv, my = sy * inv, mz = sz * inv;
             nv = fast_eigen3x3(sxx * inv - mx * mx, sxy * inv - mx * my, sxz * inv - mx * mz, syy * inv - my * my, syz * inv - my * mz,
                                szz * inv - mz * mz, &gap);
-            redo = (gap < kIllGap && cnt <= kCanon) ? 1 : 0;
         } else {
             nv = fast_eigen3x3(1, 0, 0, 1, 0, 1, &gap);   // Open3D: covariance = Identity when fewer than 3 neighbours
         }
     }
-    redo = __shfl_sync(kFull, redo, 0);
     if (redo) {
         // Ill-conditioned neighbourhood (e.g. collinear points of one scan ring): the eigenvector amplifies the
         // rounding of the covariance by 1/gap, so reproduce Open3D's arithmetic exactly: raw-coordinate cumulants,
@@ -614,16 +604,25 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
             order[rank] = key_pos[a];
         }
         __syncwarp();
-        if (lane == 0) {
-            double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
+        // the nine cumulants are independent sequential sums: lane k carries cumulant k (x, y, z, xx, xy, xz, yy, yz, zz;
+        // x * 1.0 is exact), every lane reads the same record (broadcast), so each sum keeps the oracle's order
+        double acc = 0.0;
+        {
+            const int fa = lane < 3 ? lane : (lane < 6 ? 0 : (lane < 8 ? 1 : 2));          // first factor: 0 = x, 1 = y, 2 = z
+            const int fb = lane < 3 ? 3 : (lane < 6 ? lane - 3 : (lane < 8 ? lane - 5 : 2));   // second factor, 3 = the constant 1
             for (int t = 0; t < m; ++t) {
                 double x, y, z;
                 int idx;
                 load_rec(recs + order[t], x, y, z, idx);
-                c0 = __dadd_rn(c0, x); c1 = __dadd_rn(c1, y); c2 = __dadd_rn(c2, z);
-                c3 = __dadd_rn(c3, __dmul_rn(x, x)); c4 = __dadd_rn(c4, __dmul_rn(x, y)); c5 = __dadd_rn(c5, __dmul_rn(x, z));
-                c6 = __dadd_rn(c6, __dmul_rn(y, y)); c7 = __dadd_rn(c7, __dmul_rn(y, z)); c8 = __dadd_rn(c8, __dmul_rn(z, z));
+                const double a = fa == 0 ? x : (fa == 1 ? y : z);
+                const double b = fb == 0 ? x : (fb == 1 ? y : (fb == 2 ? z : 1.0));
+                acc = __dadd_rn(acc, __dmul_rn(a, b));
             }
+        }
+        double c0 = __shfl_sync(kFull, acc, 0), c1 = __shfl_sync(kFull, acc, 1), c2 = __shfl_sync(kFull, acc, 2),
+               c3 = __shfl_sync(kFull, acc, 3), c4 = __shfl_sync(kFull, acc, 4), c5 = __shfl_sync(kFull, acc, 5),
+               c6 = __shfl_sync(kFull, acc, 6), c7 = __shfl_sync(kFull, acc, 7), c8 = __shfl_sync(kFull, acc, 8);
+        if (lane == 0) {
             const double dn = (double)m;
             c0 = __ddiv_rn(c0, dn); c1 = __ddiv_rn(c1, dn); c2 = __ddiv_rn(c2, dn); c3 = __ddiv_rn(c3, dn); c4 = __ddiv_rn(c4, dn);
             c5 = __ddiv_rn(c5, dn); c6 = __ddiv_rn(c6, dn); c7 = __ddiv_rn(c7, dn); c8 = __ddiv_rn(c8, dn);
@@ -636,6 +635,28 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
         if (sqrt(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) == 0.0) nv = {0.0, 0.0, 1.0};
         reinterpret_cast<double4*>(s.normals)[p] = make_double4(nv.x, nv.y, nv.z, 0.0);
         s.nn_count[p] = cnt;
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const ScanDev& s = scans[blockIdx.y];
+    if ((s.wide != 0) != WIDE) return;
+    const int n = s.counts[CNT_NPTS];
+    const int w = threadIdx.x >> 5;
+    if (mode == 0) {
+        const int p = blockIdx.x * kNrmWarps + w;
+        if (p < n) normals_point<WIDE>(s, np, 0, p, s_raw);
+    } else {
+        // the redo list holds a few per cent of the points: a small grid strides over it (a full-size grid of blocks that
+        // exit at once costs more than the work itself)
+        const int nredo = s.counts[CNT_NREDO];
+        for (int q = blockIdx.x * kNrmWarps + w; q < nredo; q += gridDim.x * kNrmWarps) {
+            const int p = s.redo_list[q];
+            if (p < n) normals_point<WIDE>(s, np, 1, p, s_raw);
+            __syncwarp();
+        }
     }
 }
 
@@ -684,9 +705,10 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
     if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem_sel, d_scans, np, 0);
     L.launch("normals_eigen", k_normals_eigen, dim3((cap_max + 127) / 128, n_scans), dim3(128), d_scans);
-    // ill-conditioned points (a few per cent): the grid is sized for the worst case, blocks past the list length exit
-    if (any_narrow) L.launch_smem("normals_redo", k_normals<false>, grid, block, smem, d_scans, np, 1);
-    if (any_wide) L.launch_smem("normals_redo", k_normals<true>, grid, block, smem, d_scans, np, 1);
+    // ill-conditioned points (a few per cent)
+    const dim3 grid_redo(min(grid.x, 96u), n_scans);
+    if (any_narrow) L.launch_smem("normals_redo", k_normals<false>, grid_redo, block, smem, d_scans, np, 1);
+    if (any_wide) L.launch_smem("normals_redo", k_normals<true>, grid_redo, block, smem, d_scans, np, 1);
 }
 
 }  // namespace arvc
