@@ -288,6 +288,7 @@ def main():
     value = world * P * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers -> result records on the host, every step
+    rec_all = e2e_path()      # untimed: back from the resident-scan path to the upload path (re-sizes the engine's scratch blocks)
     barrier()
     t0 = time.perf_counter()
     e2e_step_ms = []

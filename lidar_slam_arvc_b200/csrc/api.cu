@@ -111,7 +111,7 @@ struct arvc_ctx {
     void dev_put(void* p, size_t bytes) {
         if (!p) return;
         dev_free.emplace_back(bytes, p);
-        while (dev_free.size() > 6) {                    // keep the cache small: drop the smallest block
+        while (dev_free.size() > 12) {                   // keep the cache small: drop the smallest block
             size_t k = 0;
             for (size_t i = 1; i < dev_free.size(); ++i) if (dev_free[i].first < dev_free[k].first) k = i;
             cudaFreeAsync(dev_free[k].second, L.stream);
