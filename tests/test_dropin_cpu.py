@@ -233,3 +233,39 @@ def test_dropin_icp2planes_on_oracle_engine(tmp_path):
         for k in list(sys.modules):
             if k not in saved_mods:
                 del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_reference_scanmatcher_runs_icp2planes_on_dropin(tmp_path):
+    """The reference's unmodified driver with `method: icp2planes` in scanmatcher_parameters.yaml (run_scanmatcher.py:159-166):
+    every pair becomes one device batch of two registrations (ground / non-ground parts)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_engine import OracleEngine
+    seq = synth.Sequence(4, synth.TINY_16, start=30.0)
+    d = str(tmp_path / "euroc")
+    euroc_synth.write_euroc_tree(d, seq, method="icp2planes")
+    saved_path, saved_mods = list(sys.path), dict(sys.modules)
+    fake = OracleEngine()
+    runtime.set_engine(fake)
+    try:
+        _stub_missing_modules()
+        for m in [k for k in sys.modules if k.split(".")[0] in ("config", "keyframemanager")]:
+            del sys.modules[m]
+        sys.path.insert(0, REF)
+        sys.path.insert(0, DROPIN)
+        import run_scanmatcher
+        run_scanmatcher.scanmatcher(directory=d)
+        import pandas as pd
+        rel = pd.read_csv(os.path.join(d, "robot0", "scanmatcher", "scanmatcher_relative.csv"))
+        assert len(rel) == 3
+        assert [c for c in fake.calls if c[0] == "icp_batch"] == [("icp_batch", 2)] * 3
+        assert len([c for c in fake.calls if c[0] == "fit_plane"]) == 4 and len([c for c in fake.calls if c[0] == "split_plane"]) == 4
+        for i in range(3):
+            gt = seq.relative_gt(i, i + 1)
+            assert np.linalg.norm(rel.loc[i, ["x", "y", "z"]].to_numpy(dtype=float) - gt[:3, 3]) < 0.06
+    finally:
+        runtime.set_engine(None)
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]
