@@ -366,7 +366,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     const double R = std::sqrt(p->max_radius2);
     const double pad = 0.5;
     const double ext = std::max(2 * (R + pad), p->max_height - p->min_height + 2 * pad);
-    double c0 = p->grid_cell > 0 ? p->grid_cell : (getenv("ARVC_GRID_CELL") ? atof(getenv("ARVC_GRID_CELL")) : 0.075);
+    double c0 = p->grid_cell > 0 ? p->grid_cell : (getenv("ARVC_GRID_CELL") ? atof(getenv("ARVC_GRID_CELL")) : 0.09);
     const double ncell_max = (double)((1 << kMortonBits) - 1);
     if (ext / c0 > ncell_max) c0 = ext / ncell_max;
     const double max_dist = p->grid_max_dist > 0 ? p->grid_max_dist : 10.0;
@@ -785,7 +785,7 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             ip.rel_fitness = p->rel_fitness; ip.rel_rmse = p->rel_rmse; ip.max_iter = p->max_iter; ip.method = p->method;
             {
                 const char* cm = getenv("ARVC_CERT_MARGIN");      // tuning knob; results do not depend on it
-                ip.cert_margin = cm ? atof(cm) : 0.02;
+                ip.cert_margin = cm ? atof(cm) : 0.0075;
                 const char* cp = getenv("ARVC_CHUNK_PAIRS");
                 ip.chunk_pairs = cp ? atoi(cp) : 0;
                 ip.debug = getenv("ARVC_DEBUG_STATS") ? atoi(getenv("ARVC_DEBUG_STATS")) : 0;
