@@ -696,11 +696,13 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     np.debug = getenv("ARVC_DEBUG_NORMALS") ? atoi(getenv("ARVC_DEBUG_NORMALS")) : 0;
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
     const size_t smem = (size_t)kNrmWarps * kWarpSmem, smem_sel = (size_t)kNrmWarps * kWarpSmemSel;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;      // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_set >> (dev & 63)) & 1ull)) {
         cudaFuncSetAttribute(k_normals<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
     if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem_sel, d_scans, np, 0);
