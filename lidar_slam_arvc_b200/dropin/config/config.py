@@ -6,28 +6,34 @@ import os
 
 import yaml
 
+# attribute -> (yaml section, key, default); a default of ... marks a required entry
+_FIELDS = {
+    "max_radius": ("filter_by_radius", "max_radius", ...),
+    "min_radius": ("filter_by_radius", "min_radius", ...),
+    "max_height": ("filter_by_height", "max_height", ...),
+    "min_height": ("filter_by_height", "min_height", ...),
+    "voxel_size": ("down_sample", "voxel_size", None),
+    "radius_gd": ("filter_ground_plane", "radius_normals", ...),
+    "max_nn_gd": ("filter_ground_plane", "maximum_neighbors", ...),
+    "radius_normals": ("normals", "radius_normals", ...),
+    "max_nn": ("normals", "maximum_neighbors", ...),
+    "distance_threshold": ("icp", "distance_threshold", ...),
+    "relative_fitness": ("icp_criteria", "relative_fitness", 1e-6),
+    "relative_rmse": ("icp_criteria", "relative_rmse", 1e-6),
+    "max_iteration": ("icp_criteria", "max_iteration", 30),
+}
+
 
 class Icp_parameters():
     def __init__(self, yaml_file='icp_parameters.yaml'):
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), yaml_file)
-        with open(path) as file:
-            cfg = yaml.load(file, Loader=yaml.FullLoader)
-        by_radius = cfg.get('filter_by_radius')
-        by_height = cfg.get('filter_by_height')
-        self.max_radius = by_radius.get('max_radius')
-        self.min_radius = by_radius.get('min_radius')
-        self.max_height = by_height.get('max_height')
-        self.min_height = by_height.get('min_height')
-        self.voxel_size = cfg.get('down_sample').get('voxel_size')
-        self.radius_gd = cfg.get('filter_ground_plane').get('radius_normals')
-        self.max_nn_gd = cfg.get('filter_ground_plane').get('maximum_neighbors')
-        self.radius_normals = cfg.get('normals').get('radius_normals')
-        self.max_nn = cfg.get('normals').get('maximum_neighbors')
-        self.distance_threshold = cfg.get('icp').get('distance_threshold')
-        crit = cfg.get('icp_criteria') or {}
-        self.relative_fitness = crit.get('relative_fitness', 1e-6)
-        self.relative_rmse = crit.get('relative_rmse', 1e-6)
-        self.max_iteration = crit.get('max_iteration', 30)
+        here = os.path.dirname(os.path.abspath(__file__))
+        with open(os.path.join(here, yaml_file)) as stream:
+            tree = yaml.safe_load(stream) or {}
+        for attr, (section, key, default) in _FIELDS.items():
+            value = (tree.get(section) or {}).get(key, default)
+            if value is ...:
+                raise KeyError("icp_parameters.yaml: missing %s.%s" % (section, key))
+            setattr(self, attr, value)
 
 
 ICP_PARAMETERS = Icp_parameters()
