@@ -309,10 +309,12 @@ def main():
 
     # ---- roofline of the dominant kernel (device events recorded around every launch of the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (KeyError, ValueError, TypeError):
+        pass
     total_kernel_ms = sum(v[1] for v in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
     name, (n_launch, tot_ms) = dom
