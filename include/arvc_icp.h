@@ -45,6 +45,10 @@ const char* arvc_last_error(const arvc_ctx* ctx); /* ctx may be NULL: error of t
 int arvc_sync(arvc_ctx* ctx);                     /* wait for all queued work of the context */
 void* arvc_stream(arvc_ctx* ctx);                 /* the context's cudaStream_t (for event timing) */
 int arvc_version(void);
+/* Engine switches (0 / 1), for A/B measurements and parity tests; results never depend on them:
+ *   "icp_loop_graph"  1 (default): registration loops are ONE CUDA graph whose WHILE node ends the iteration on the
+ *                     device with the last convergence; 0: max_iter + 1 passes are enqueued unconditionally. */
+int arvc_ctx_set_option(arvc_ctx* ctx, const char* name, int value);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t arvc_kernel_launches(const arvc_ctx* ctx);
 /* Per-kernel device timing with CUDA events on the context stream (bench.py's roofline line).  enable(1) starts
@@ -119,6 +123,10 @@ int arvc_scan_split_plane(arvc_ctx* ctx, int64_t src_id, const double* plane /* 
 int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index);
 int arvc_scan_get_voxels(arvc_ctx* ctx, int64_t scan_id, int32_t* keys, int32_t* counts);
 int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count);
+/* Device counters of a preprocessed scan, counters[16]: 0 points after the filter, 1 final points, 2 error flags,
+ * 3 occupied grid cells (all levels), 4 normals recomputed in canonical order, 5 points served by the per-point
+ * normals kernel, 6 blocks / 7 single points the block kernel handed back, 8 blocks served at a trial radius. */
+int arvc_scan_get_counters(arvc_ctx* ctx, int64_t scan_id, int32_t* counters);
 
 /* --- registration ---------------------------------------------------------------------------------- */
 typedef struct arvc_icp_params {

@@ -45,6 +45,7 @@ struct PendingBatch {
     PairState* d_states = nullptr;
     PairState* h_states = nullptr;   // pinned, from the context's pool
     size_t h_bytes = 0;
+    const IcpGraph* graph = nullptr; // the device-terminated loop this batch was enqueued with (launch accounting)
 };
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -70,6 +71,8 @@ struct arvc_ctx {
     std::map<uint64_t, PendingBatch> pending;
     uint64_t next_ticket = 1;
     std::vector<std::pair<size_t, void*>> pinned_free;   // recycled pinned staging buffers
+    IcpGraphCache icp_graphs;
+    bool icp_use_graph = true;          // ARVC_ICP_LOOP=unrolled / arvc_ctx_set_option("icp_loop_graph", 0) switch it off
 
     void* pinned_get(size_t bytes, size_t* got) {
         for (size_t i = 0; i < pinned_free.size(); ++i)
@@ -222,6 +225,7 @@ void plan_scratch(SlabPlanner& P, ScanDev& d, int n_raw, bool voxel_on) {
     d.bbox = P.take<double>(8);
     d.moments = P.take<double>(cap * 10);
     d.redo_list = P.take<int>(cap);
+    d.fb_list = P.take<int>(cap);
 }
 
 __global__ void k_clear_scan(const ScanDev* __restrict__ scans) {
@@ -263,13 +267,23 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    const char* loop = getenv("ARVC_ICP_LOOP");
+    if (loop && std::string(loop) == "unrolled") ctx->icp_use_graph = false;
     *out = ctx;
     return ARVC_OK;
+}
+
+int arvc_ctx_set_option(arvc_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return ARVC_E_ARG;
+    if (std::string(name) == "icp_loop_graph") { ctx->icp_use_graph = value != 0; return ARVC_OK; }
+    return ctx->fail(ARVC_E_ARG, std::string("ctx_set_option: unknown option ") + name);
 }
 
 void arvc_ctx_destroy(arvc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->L.stream);
+    icp_graphs_destroy(ctx->icp_graphs);
     for (auto& df : ctx->dev_free) cudaFreeAsync(df.second, ctx->L.stream);
     for (auto& kv : ctx->pending) {
         if (kv.second.slab) cudaFreeAsync(kv.second.slab, ctx->L.stream);
@@ -375,7 +389,6 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     g.c0 = c0; g.inv_c0 = 1.0 / c0;
     g.top_level = 0;
     while (g.top_level < kMortonBits && c0 * (double)(1 << g.top_level) < max_dist * 1.001) ++g.top_level;
-    g.cold_level = std::min(1, g.top_level);
     NormalParams np{};
     np.radius = p->normal_radius; np.max_nn = p->max_nn; np.level = 0;
     if (want_normals)
@@ -714,6 +727,17 @@ int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count) {
     return ARVC_OK;
 }
 
+int arvc_scan_get_counters(arvc_ctx* ctx, int64_t scan_id, int32_t* counters) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed || !counters) return ctx->fail(ARVC_E_STATE, "scan_get_counters: scan not preprocessed");
+    CK(cudaSetDevice(ctx->device));
+    static_assert(CNT_WORDS == 16, "arvc_scan_get_counters documents 16 words");
+    CK(cudaMemcpyAsync(counters, s->dev.counts, sizeof(int) * CNT_WORDS, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return ARVC_OK;
+}
+
 // ---- registration --------------------------------------------------------------------------------------
 static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
                        const arvc_icp_params* p, bool trace, PendingBatch& pb, int** d_corr_trace, double** d_state_trace,
@@ -746,6 +770,7 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
         P.base = pass ? reinterpret_cast<char*>(pb.slab) : nullptr;
         PairDev* d_pairs = P.take<PairDev>(n_pairs);
         PairState* d_states = P.take<PairState>(n_pairs);
+        BatchDesc* d_bd = P.take<BatchDesc>(1);
         std::vector<PairDev> hp(pass ? n_pairs : 0);
         for (int i = 0; i < n_pairs; ++i) {
             const size_t cap = (size_t)S[i]->dev.cap;
@@ -779,18 +804,18 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             }
             CK(cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
             CK(cudaMemcpyAsync(d_states, pb.h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
-            IcpParams ip{};
+            BatchDesc bd{};
+            bd.pairs = d_pairs; bd.n_pairs = n_pairs;
+            IcpParams& ip = bd.ip;
             ip.max_d = p->max_corr_dist;
             ip.max_d2 = p->max_corr_dist > 0 ? p->max_corr_dist * p->max_corr_dist : 0.0;
             ip.rel_fitness = p->rel_fitness; ip.rel_rmse = p->rel_rmse; ip.max_iter = p->max_iter; ip.method = p->method;
             {
                 const char* cm = getenv("ARVC_CERT_MARGIN");      // tuning knob; results do not depend on it
                 ip.cert_margin = cm ? atof(cm) : 0.0075;
-                const char* cp = getenv("ARVC_CHUNK_PAIRS");
-                ip.chunk_pairs = cp ? atoi(cp) : 0;
                 ip.debug = getenv("ARVC_DEBUG_STATS") ? atoi(getenv("ARVC_DEBUG_STATS")) : 0;
             }
-            run_icp(ctx->L, d_pairs, n_pairs, src_cap_max, ip, combos);
+            pb.graph = run_icp(ctx->L, ctx->icp_graphs, bd, d_bd, src_cap_max, combos, ctx->icp_use_graph);
             static_assert(offsetof(PairState, Thist) == kPairStateHead, "PairState head layout");
             CK(cudaMemcpy2DAsync(pb.h_states, sizeof(PairState), d_states, sizeof(PairState), kPairStateHead, n_pairs,
                                  cudaMemcpyDeviceToHost, ctx->L.stream));
@@ -819,6 +844,11 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
         }
         fprintf(stderr, "[arvc stats] pairs=%d passes=%lld queries=%llu searched=%llu (union=%llu fallback=%llu)\n", pb.n_pairs, passes,
                 tot[3], tot[0], tot[1], tot[2]);
+    }
+    if (pb.graph) {      // kernels the device-terminated loop executed: the prefix + one body per pass beyond it
+        int max_passes = 0;
+        for (int i = 0; i < pb.n_pairs; ++i) max_passes = std::max(max_passes, pb.h_states[i].passes);
+        ctx->L.launches += pb.graph->kernels_prefix + (long long)pb.graph->kernels_body * std::max(0, max_passes - kIcpUnrolled);
     }
     for (int i = 0; i < pb.n_pairs; ++i) {
         const PairState& st = pb.h_states[i];

@@ -61,7 +61,7 @@ struct GridSpec {
     double inv_c0;       // 1 / finest cell edge
     double c0;
     int top_level;       // coarsest level a search may use
-    int cold_level;      // level a search without a previous match starts at
+    int pad;
 };
 
 struct __align__(16) HashEntry { unsigned long long key; unsigned start; unsigned end; };
@@ -110,7 +110,12 @@ __device__ __forceinline__ bool grid_lookup(const HashEntry* __restrict__ tab, u
 }
 
 // ---- per-scan device view ------------------------------------------------------------------------------
-enum { CNT_NFILT = 0, CNT_NPTS = 1, CNT_ERR = 2, CNT_NCELLS = 3, CNT_NREDO = 4, CNT_WORDS = 8 };
+enum { CNT_NFILT = 0, CNT_NPTS = 1, CNT_ERR = 2, CNT_NCELLS = 3, CNT_NREDO = 4,
+       CNT_NFB = 5,             // points on the normals fallback list (served by the per-point kernel)
+       CNT_NFB_BLOCKS = 6,      // statistics: blocks of k_normals_blk that fell back as a whole
+       CNT_NFB_POINTS = 7,      //             single points that fell back (trial radius too small, boundary overflow)
+       CNT_NTRIAL_BLOCKS = 8,   //             blocks served at a trial radius
+       CNT_WORDS = 16 };
 enum { ERR_HASH_FULL = 1, ERR_VOXEL_RANGE = 2 };
 
 struct ScanDev {
@@ -142,6 +147,7 @@ struct ScanDev {
     double* bbox;           // [8] min bound / origin of the voxel grid
     double* moments;        // [cap][10] centred moment sums + neighbour count per point (normals)
     int* redo_list;         // [cap] points whose normal needs the canonical re-summation
+    int* fb_list;           // [cap] points the block kernel hands to the per-point kernel
 };
 
 // ---- warp helpers ------------------------------------------------------------------------------------------

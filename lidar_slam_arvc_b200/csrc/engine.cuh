@@ -35,6 +35,17 @@ struct Launcher {
         cudaEventCreate(&e);
         return e;
     }
+    // the same, for a kernel given as a plain function pointer with an argument array (shared with the graph builder)
+    void launch_ptr(const char* name, const void* func, dim3 grid, dim3 block, void** args) {
+        if (err != cudaSuccess) return;
+        if (grid.x == 0 || grid.y == 0) return;
+        Rec r{name, nullptr, nullptr};
+        if (profile) { r.a = get_event(); r.b = get_event(); cudaEventRecord(r.a, stream); }
+        const cudaError_t e = cudaLaunchKernel(func, grid, block, args, 0, stream);
+        if (profile) { cudaEventRecord(r.b, stream); recs.push_back(r); }
+        if (e != cudaSuccess) err = e;
+        ++launches;
+    }
     template <typename... KArgs, typename... Args>
     void launch(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
         launch_smem(name, kernel, grid, block, 0, args...);
@@ -94,16 +105,46 @@ struct IcpParams {
     int max_iter;
     int method;
     int debug;              // collect search statistics into PairState (ARVC_DEBUG_STATS)
-    int chunk_pairs;        // pairs iterated together (0 = whole batch)
+    int pad;
 };
 
 constexpr int kSumStride = 32;
 constexpr int kIcpBlock = 64;
+constexpr int kIcpUnrolled = 4;     // passes enqueued as plain nodes before the device-terminated loop takes over
+
+// Everything the ICP kernels need to know about the batch, in device memory: the kernels' only argument, so that one
+// instantiated CUDA graph (fixed arguments) serves every batch of the same shape.
+struct BatchDesc {
+    const PairDev* pairs;
+    int n_pairs;
+    int pad;
+    IcpParams ip;
+};
+
+// Instantiated ICP graphs of a context, keyed by batch shape: unrolled passes 0..kIcpUnrolled-1, then a conditional
+// WHILE node whose body is one pass and whose condition ("some pair has not converged") is set on the device.
+struct IcpGraph {
+    unsigned long long key = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int kernels_prefix = 0, kernels_body = 0;
+};
+struct IcpGraphCache {
+    std::vector<IcpGraph> graphs;
+    BatchDesc* d_bd = nullptr;          // fixed address the graphs' kernels read the current batch from
+    bool disabled = false;              // graph construction failed once: stay on the unrolled path
+    std::string error;
+};
 
 void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const FilterParams& fp, const VoxelParams& vp,
                     bool voxel_on);
 void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow);
-void run_icp(Launcher& L, const PairDev* d_pairs, int n_pairs, int src_cap_max, const IcpParams& ip, int combos_mask);
+void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np);
+// Enqueues the whole iteration of a batch.  `use_graph`: device-terminated loop (CUDA graph with a WHILE node); else
+// max_iter + 1 passes are enqueued unconditionally (finished pairs turn into no-ops).  Returns the graph used (or null).
+const IcpGraph* run_icp(Launcher& L, IcpGraphCache& cache, const BatchDesc& h_bd, BatchDesc* d_bd_batch, int src_cap_max, int combos_mask,
+                        bool use_graph);
+void icp_graphs_destroy(IcpGraphCache& cache);
 void run_plane_fit(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_score, double* d_result, double max_z, double thr,
                    int iters, unsigned long long seed);
 void run_plane_split(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_blk, double* d_near, double* d_far, int* d_counts2,

@@ -1,13 +1,20 @@
-// ICP iteration, fully device-resident: one fused pass kernel per iteration does
-//   source transform -> exact nearest neighbour on the target's hash grid (warm-started from the previous
-//   pass' match) -> residual/Jacobian (point-to-plane) or Umeyama moments (point-to-point) ->
-//   warp + block reduction -> last-block grid reduction -> 6x6 LDLT / 3x3 SVD solve -> update of the
-//   cumulative transformation and Open3D's convergence test.
-// The host only enqueues max_iter+1 launches; converged pairs turn into no-ops via a device flag.
+// ICP iteration, fully device-resident.  One pass over a batch of pairs = four kernels:
+//   k_icp_select  (passes > 0) nearest-neighbour certificates: which source points need a new search;
+//   k_icp_search  exact nearest neighbour on the target's multi-resolution hash grid for those points;
+//   k_icp_accum   residual / Jacobian (point-to-plane) or Umeyama moments (point-to-point) of the matches, fixed-order
+//                 warp reduction into one row of partial sums per warp;
+//   k_icp_finish  per pair: reduction of the rows, 6x6 LDLT / 3x3 SVD solve, update of the cumulative transformation
+//                 and Open3D's convergence test.
+// The host enqueues ONE CUDA graph per batch: the first kIcpUnrolled passes as plain kernel nodes, then a conditional
+// WHILE node whose body is one pass and whose condition - "some pair of the batch has not converged" - is set on the
+// device (k_icp_cond), so the iteration ends with the last convergence and without any host round trip.
+// (ARVC_ICP_LOOP=unrolled: max_iter + 1 passes enqueued unconditionally; finished pairs turn into no-ops.)
 //
 // Reference semantics restated: keyframemanager/keyframe.py:246-252 -> Open3D RegistrationICP,
 // GetRegistrationResultAndCorrespondences, TransformationEstimationPointToPlane / PointToPoint.
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "engine.cuh"
 
@@ -351,10 +358,12 @@ __device__ void solve_update(int method, const double* S, double* upd) {
 //                 warp reduction into one row of partial sums per warp (bit-reproducible run to run).
 // ---------------------------------------------------------------------------------------------------
 template <bool SW, bool TW>
-__global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+__global__ void __launch_bounds__(256) k_icp_select(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
-    const PairDev& pr = pairs[blockIdx.y];
+    if ((int)blockIdx.y >= bd->n_pairs) return;
+    const PairDev& pr = bd->pairs[blockIdx.y];
+    const double ip_max_d2 = bd->ip.max_d2;
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
         const double sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
         const double sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
         const double sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-        need = (sx == sx && sy == sy && sz == sz) && ip.max_d2 > 0;
+        need = (sx == sx && sy == sy && sz == sz) && ip_max_d2 > 0;
         const int pv = pr.prev[i];
         const int c = pr.cert_pass[i];
         if (need && pv >= 0 && c != 255) {
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
             const double ez = sz - (Tc[8] * px + Tc[9] * py + Tc[10] * pz + Tc[11]);
             const double delta = sqrt(ex * ex + ey * ey + ez * ez);
             const double br = sqrt(d2) * (1.0 + 1e-9) + 1e-12;
-            if (d2 < ip.max_d2 && (br + delta) * (1.0 + 1e-7) + 1e-9 < (double)pr.lb2[i]) need = false;
+            if (d2 < ip_max_d2 && (br + delta) * (1.0 + 1e-7) + 1e-9 < (double)pr.lb2[i]) need = false;
         }
     }
     // block-ordered append, padded to a multiple of kG with -1: the kG entries a search group serves then always come
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(256) k_icp_select(const PairDev* __restrict__ 
 }
 
 template <bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+__global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
@@ -421,12 +430,15 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const PairDev* __restr
     __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
     __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
 
-    const PairDev& pr = pairs[blockIdx.y];
+    if ((int)blockIdx.y >= bd->n_pairs) return;
+    const PairDev& pr = bd->pairs[blockIdx.y];
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
+    const int pass = st->passes;         // completed passes = index of this one
+    struct { double max_d2, cert_margin; int debug; } ip = {bd->ip.max_d2, bd->ip.cert_margin, bd->ip.debug};
     const int n = pass == 0 ? src.counts[CNT_NPTS] : st->nlist;       // pass 0 searches every point
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
     const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
@@ -731,15 +743,17 @@ constexpr int kAccPts = 4;                                  // source points per
 constexpr int kAccBlockPts = kIcpBlock * kAccPts;
 
 template <int METHOD, bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+__global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
-    const PairDev& pr = pairs[blockIdx.y];
+    if ((int)blockIdx.y >= bd->n_pairs) return;
+    const PairDev& pr = bd->pairs[blockIdx.y];
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
+    const int pass = st->passes;
     const int n = src.counts[CNT_NPTS];
     const int nblk = max(1, (n + kAccBlockPts - 1) / kAccBlockPts);
     const int lane = lane_id();
@@ -817,12 +831,15 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_accum(const PairDev* __restri
 // Finish kernel, one block per pair: fixed-order reduction of the warps' partial sums, solve, cumulative
 // transformation update and Open3D's convergence test.  Sets the `done` flag that turns later passes into no-ops.
 template <int METHOD>
-__global__ void __launch_bounds__(256) k_icp_finish(const PairDev* __restrict__ pairs, IcpParams ip, int pass) {
+__global__ void __launch_bounds__(256) k_icp_finish(const BatchDesc* __restrict__ bd) {
     __shared__ double s_part[8][kSumStride];
     __shared__ double s_sum[kSumStride];
-    const PairDev& pr = pairs[blockIdx.x];
+    if ((int)blockIdx.x >= bd->n_pairs) return;
+    const PairDev& pr = bd->pairs[blockIdx.x];
     PairState* st = pr.state;
     if (st->done) return;
+    const int pass = st->passes;
+    const IcpParams ip = bd->ip;
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     const int n = src.counts[CNT_NPTS];
@@ -871,7 +888,17 @@ __global__ void __launch_bounds__(256) k_icp_finish(const PairDev* __restrict__ 
     }
 }
 
-static const char* pass_name(int pass) {   // "icp_pass_00" ... so that the profile report separates the passes
+// WHILE condition of the device-terminated loop: non-zero while some pair of the batch has not converged.
+__global__ void __launch_bounds__(256) k_icp_cond(const BatchDesc* __restrict__ bd, cudaGraphConditionalHandle handle) {
+    int open_pairs = 0;
+    for (int i = threadIdx.x; i < bd->n_pairs; i += blockDim.x) open_pairs |= bd->pairs[i].state->done ? 0 : 1;
+    const int any = __syncthreads_or(open_pairs);
+    if (threadIdx.x == 0) cudaGraphSetConditional(handle, any ? 1u : 0u);
+}
+
+namespace {
+
+const char* pass_name(int pass) {   // "icp_pass_00" ... so that the profile report separates the passes
     static char names[64][16];
     static bool init = false;
     if (!init) {
@@ -881,46 +908,154 @@ static const char* pass_name(int pass) {   // "icp_pass_00" ... so that the prof
     return names[pass < 63 ? pass : 63];
 }
 
-template <int METHOD>
-static void launch_combos(Launcher& L, const PairDev* d_pairs, dim3 grid, int cap_max, const IcpParams& ip, int pass, int combos_mask) {
-    const char* nm = pass_name(pass);
-    // Pairs converge after ~5-12 passes but max_iter + 1 are enqueued (no host round trip): the later the pass, the
-    // smaller the grid, so that the blocks of finished pairs cost next to nothing; the kernels stride over their chunks.
-    const int sh_pts = pass < 4 ? 0 : (pass < 10 ? 2 : 3), sh_search = pass < 3 ? 0 : (pass < 5 ? 1 : 2);
-    const dim3 g256(max(1, ((cap_max + 255) / 256) >> sh_pts), grid.y);
-    grid.x = max(1u, grid.x >> sh_search);
-    if (pass > 0) {
-        if (combos_mask & 1) L.launch("icp_select", k_icp_select<false, false>, g256, dim3(256), d_pairs, ip, pass);
-        if (combos_mask & 2) L.launch("icp_select", k_icp_select<false, true>, g256, dim3(256), d_pairs, ip, pass);
-        if (combos_mask & 4) L.launch("icp_select", k_icp_select<true, false>, g256, dim3(256), d_pairs, ip, pass);
-        if (combos_mask & 8) L.launch("icp_select", k_icp_select<true, true>, g256, dim3(256), d_pairs, ip, pass);
+// Receives the kernels of one pass in order: either launches them on the stream or chains them as graph nodes.
+struct Emitter {
+    Launcher* L = nullptr;                      // stream mode
+    cudaGraph_t graph = nullptr;                // graph mode
+    cudaGraphNode_t last = nullptr;
+    cudaError_t err = cudaSuccess;
+    int count = 0;
+    void kernel(const char* name, const void* func, dim3 grid, dim3 block, void** args) {
+        ++count;
+        if (L) { L->launch_ptr(name, func, grid, block, args); return; }
+        if (err != cudaSuccess) return;
+        cudaKernelNodeParams kp{};
+        kp.func = const_cast<void*>(func);
+        kp.gridDim = grid; kp.blockDim = block; kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+        cudaGraphNode_t node = nullptr;
+        err = cudaGraphAddKernelNode(&node, graph, last ? &last : nullptr, last ? 1 : 0, &kp);
+        last = node;
     }
-    if (combos_mask & 1) L.launch(nm, k_icp_search<false, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch(nm, k_icp_search<false, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch(nm, k_icp_search<true, false>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch(nm, k_icp_search<true, true>, grid, dim3(kIcpBlock), d_pairs, ip, pass);
-    const dim3 gacc(max(1, ((cap_max + kAccBlockPts - 1) / kAccBlockPts) >> sh_pts), grid.y);
-    if (combos_mask & 1) L.launch("icp_accum", k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 2) L.launch("icp_accum", k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 4) L.launch("icp_accum", k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
-    if (combos_mask & 8) L.launch("icp_accum", k_icp_accum<METHOD, true, true>, gacc, dim3(kIcpBlock), d_pairs, ip, pass);
-    L.launch("icp_finish", k_icp_finish<METHOD>, dim3(grid.y), dim3(256), d_pairs, ip, pass);
+};
+
+// Pairs converge after ~5-12 passes: the later the pass, the smaller the grid (the kernels stride over their chunks),
+// so that the blocks of finished pairs cost next to nothing.  `pass` >= kIcpUnrolled stands for the loop body.
+template <int METHOD>
+void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, int n_pairs_grid, int pass, int combos_mask) {
+    const char* nm = pass_name(pass);
+    const int sh_pts = pass < 4 ? 0 : (pass < 10 ? 2 : 3), sh_search = pass < 3 ? 0 : (pass < 5 ? 1 : 2);
+    const dim3 g256(max(1, ((cap_max + 255) / 256) >> sh_pts), n_pairs_grid);
+    const dim3 gsearch(max(1, gx_search >> sh_search), n_pairs_grid);
+    const dim3 gacc(max(1, ((cap_max + kAccBlockPts - 1) / kAccBlockPts) >> sh_pts), n_pairs_grid);
+    void* args[] = {(void*)&d_bd};
+    if (pass > 0) {
+        if (combos_mask & 1) E.kernel("icp_select", (const void*)k_icp_select<false, false>, g256, dim3(256), args);
+        if (combos_mask & 2) E.kernel("icp_select", (const void*)k_icp_select<false, true>, g256, dim3(256), args);
+        if (combos_mask & 4) E.kernel("icp_select", (const void*)k_icp_select<true, false>, g256, dim3(256), args);
+        if (combos_mask & 8) E.kernel("icp_select", (const void*)k_icp_select<true, true>, g256, dim3(256), args);
+    }
+    if (combos_mask & 1) E.kernel(nm, (const void*)k_icp_search<false, false>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel(nm, (const void*)k_icp_search<false, true>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 1) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, true>, gacc, dim3(kIcpBlock), args);
+    E.kernel("icp_finish", (const void*)k_icp_finish<METHOD>, dim3(n_pairs_grid), dim3(256), args);
+}
+
+void emit_pass_m(Emitter& E, int method, const BatchDesc* d_bd, int gx_search, int cap_max, int n_pairs_grid, int pass, int combos_mask) {
+    if (method == 1) emit_pass<1>(E, d_bd, gx_search, cap_max, n_pairs_grid, pass, combos_mask);
+    else emit_pass<0>(E, d_bd, gx_search, cap_max, n_pairs_grid, pass, combos_mask);
+}
+
+// batch shapes are bucketed so that a handful of instantiated graphs serves every batch size
+int bucket_pairs(int n) {
+    if (n <= 8) return n;
+    if (n <= 64) return (n + 7) / 8 * 8;
+    if (n <= 512) return (n + 31) / 32 * 32;
+    return (n + 255) / 256 * 256;
+}
+int bucket_cap(int cap) { return (cap + 4095) / 4096 * 4096; }
+
+const IcpGraph* get_graph(IcpGraphCache& cache, int method, int combos_mask, int cap_b, int pairs_b) {
+    const unsigned long long key = ((unsigned long long)method << 60) | ((unsigned long long)combos_mask << 56) |
+                                   ((unsigned long long)pairs_b << 32) | (unsigned long long)cap_b;
+    for (const IcpGraph& g : cache.graphs) if (g.key == key) return &g;
+    IcpGraph G;
+    G.key = key;
+    auto fail = [&](cudaError_t e, const char* what) -> const IcpGraph* {
+        cache.error = std::string(what) + ": " + cudaGetErrorString(e);
+        cache.disabled = true;
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        if (G.graph) cudaGraphDestroy(G.graph);
+        cudaGetLastError();
+        return nullptr;
+    };
+    cudaError_t e = cudaGraphCreate(&G.graph, 0);
+    if (e != cudaSuccess) return fail(e, "cudaGraphCreate");
+    const int gx_search = max(1, (cap_b + kIcpBlock - 1) / kIcpBlock);
+    const BatchDesc* d_bd = cache.d_bd;
+    Emitter E;
+    E.graph = G.graph;
+    for (int pass = 0; pass < kIcpUnrolled; ++pass) emit_pass_m(E, method, d_bd, gx_search, cap_b, pairs_b, pass, combos_mask);
+    if (E.err != cudaSuccess) return fail(E.err, "cudaGraphAddKernelNode");
+    cudaGraphConditionalHandle handle;
+    e = cudaGraphConditionalHandleCreate(&handle, G.graph, 1, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) return fail(e, "cudaGraphConditionalHandleCreate");
+    void* cargs[] = {(void*)&d_bd, (void*)&handle};
+    E.kernel("icp_cond", (const void*)k_icp_cond, dim3(1), dim3(256), cargs);
+    if (E.err != cudaSuccess) return fail(E.err, "cudaGraphAddKernelNode(cond)");
+    G.kernels_prefix = E.count;
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t wnode = nullptr;
+    e = cudaGraphAddNode(&wnode, G.graph, &E.last, 1, &cp);
+    if (e != cudaSuccess) return fail(e, "cudaGraphAddNode(conditional while)");
+    Emitter B;
+    B.graph = cp.conditional.phGraph_out[0];
+    emit_pass_m(B, method, d_bd, gx_search, cap_b, pairs_b, kIcpUnrolled + 1, combos_mask);      // grid shape of passes >= 5
+    B.kernel("icp_cond", (const void*)k_icp_cond, dim3(1), dim3(256), cargs);
+    if (B.err != cudaSuccess) return fail(B.err, "cudaGraphAddKernelNode(body)");
+    G.kernels_body = B.count;
+    e = cudaGraphInstantiate(&G.exec, G.graph, 0);
+    if (e != cudaSuccess) return fail(e, "cudaGraphInstantiate");
+    cache.graphs.push_back(G);
+    return &cache.graphs.back();
+}
+
+}  // namespace
+
+void icp_graphs_destroy(IcpGraphCache& cache) {
+    for (IcpGraph& g : cache.graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    cache.graphs.clear();
+    if (cache.d_bd) cudaFree(cache.d_bd);
+    cache.d_bd = nullptr;
 }
 
 // combos_mask bit (2*src_wide + tgt_wide) set when some pair of the batch has that record-type combination
-void run_icp(Launcher& L, const PairDev* d_pairs, int n_pairs, int src_cap_max, const IcpParams& ip, int combos_mask) {
-    if (n_pairs == 0) return;
-    // Pairs are iterated in chunks small enough for their scans, grids and normals (~8 MB per pair) to stay L2
-    // resident between consecutive passes; a batch-wide pass would stream the whole batch through L2 every pass.
-    const int chunk = ip.chunk_pairs > 0 ? ip.chunk_pairs : n_pairs;
-    for (int c0 = 0; c0 < n_pairs; c0 += chunk) {
-        const int nc = min(chunk, n_pairs - c0);
-        const dim3 grid(max(1, (src_cap_max + kIcpBlock - 1) / kIcpBlock), nc);
-        for (int pass = 0; pass <= ip.max_iter; ++pass) {
-            if (ip.method == 1) launch_combos<1>(L, d_pairs + c0, grid, src_cap_max, ip, pass, combos_mask);
-            else launch_combos<0>(L, d_pairs + c0, grid, src_cap_max, ip, pass, combos_mask);
+const IcpGraph* run_icp(Launcher& L, IcpGraphCache& cache, const BatchDesc& h_bd, BatchDesc* d_bd_batch, int src_cap_max, int combos_mask,
+                        bool use_graph) {
+    if (h_bd.n_pairs == 0 || L.err != cudaSuccess) return nullptr;
+    const int method = h_bd.ip.method;
+    if (use_graph && !cache.disabled) {
+        if (!cache.d_bd && cudaMalloc(&cache.d_bd, sizeof(BatchDesc)) != cudaSuccess) { cache.disabled = true; cache.error = "cudaMalloc(BatchDesc)"; cudaGetLastError(); }
+        const IcpGraph* G = cache.disabled ? nullptr : get_graph(cache, method, combos_mask, bucket_cap(src_cap_max), bucket_pairs(h_bd.n_pairs));
+        if (G) {
+            // the graph's kernels read the batch from the context's fixed descriptor: stream-ordered update, then one launch
+            cudaError_t e = cudaMemcpyAsync(cache.d_bd, &h_bd, sizeof(BatchDesc), cudaMemcpyHostToDevice, L.stream);
+            Launcher::Rec r{"icp_graph", nullptr, nullptr};
+            if (L.profile) { r.a = L.get_event(); r.b = L.get_event(); cudaEventRecord(r.a, L.stream); }
+            if (e == cudaSuccess) e = cudaGraphLaunch(G->exec, L.stream);
+            if (L.profile) { cudaEventRecord(r.b, L.stream); L.recs.push_back(r); }
+            if (e != cudaSuccess) L.err = e;
+            return G;
         }
+        fprintf(stderr, "[arvc] device-terminated ICP loop unavailable (%s): enqueuing max_iter + 1 passes instead\n", cache.error.c_str());
     }
+    if (cudaMemcpyAsync(d_bd_batch, &h_bd, sizeof(BatchDesc), cudaMemcpyHostToDevice, L.stream) != cudaSuccess) { L.err = cudaGetLastError(); return nullptr; }
+    Emitter E;
+    E.L = &L;
+    const int gx_search = max(1, (src_cap_max + kIcpBlock - 1) / kIcpBlock);
+    for (int pass = 0; pass <= h_bd.ip.max_iter; ++pass) emit_pass_m(E, method, d_bd_batch, gx_search, src_cap_max, h_bd.n_pairs, pass, combos_mask);
+    return nullptr;
 }
 
 }  // namespace arvc

@@ -8,6 +8,7 @@
 // finds the bucket holding the k-th neighbour, the bucket is ranked exactly by (d2, index).
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "engine.cuh"
 
@@ -648,6 +649,14 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
     if (mode == 0) {
         const int p = blockIdx.x * kNrmWarps + w;
         if (p < n) normals_point<WIDE>(s, np, 0, p, s_raw);
+    } else if (mode == 2) {
+        // the points the block kernel (normals_blk.cu) could not serve from its shared tile: same search, per point
+        const int nfb = s.counts[CNT_NFB];
+        for (int q = blockIdx.x * kNrmWarps + w; q < nfb; q += gridDim.x * kNrmWarps) {
+            const int p = s.fb_list[q];
+            if (p < n) normals_point<WIDE>(s, np, 0, p, s_raw);
+            __syncwarp();
+        }
     } else {
         // the redo list holds a few per cent of the points: a small grid strides over it (a full-size grid of blocks that
         // exit at once costs more than the work itself)
@@ -704,7 +713,14 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
         cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set |= 1ull << (dev & 63);
     }
-    if (any_narrow) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
+    // float32 records (the PCD payload, voxel off): block-cooperative kernel + per-point kernel for what it hands back;
+    // float64 records (voxel means, float64 uploads): per-point kernel.  ARVC_NORMALS_IMPL=point forces the latter.
+    static const bool per_point_only = getenv("ARVC_NORMALS_IMPL") && std::string(getenv("ARVC_NORMALS_IMPL")) == "point";
+    if (any_narrow && per_point_only) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
+    if (any_narrow && !per_point_only) {
+        launch_normals_blk(L, d_scans, n_scans, cap_max, np);
+        L.launch_smem("normals_fallback", k_normals<false>, dim3(min(grid.x, 192u), n_scans), block, smem_sel, d_scans, np, 2);
+    }
     if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem_sel, d_scans, np, 0);
     L.launch("normals_eigen", k_normals_eigen, dim3((cap_max + 127) / 128, n_scans), dim3(128), d_scans);
     // ill-conditioned points (a few per cent)

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
-    "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane",
+    "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane", "arvc_ctx_set_option", "arvc_scan_get_counters",
 ]
 
 
@@ -78,6 +78,8 @@ def load_library():
     lib.arvc_scan_get_filter_indices.argtypes = [vp, c.c_int64, ip]
     lib.arvc_scan_get_voxels.argtypes = [vp, c.c_int64, ip, ip]
     lib.arvc_scan_get_nn_counts.argtypes = [vp, c.c_int64, ip]
+    lib.arvc_scan_get_counters.argtypes = [vp, c.c_int64, ip]
+    lib.arvc_ctx_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.arvc_icp_batch.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), dp, dp, dp, ip, ip]
     lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
     lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
@@ -246,6 +248,19 @@ class Engine:
         cnt = np.empty(max(n, 1), dtype=np.int32)
         self._ck(self.lib.arvc_scan_get_nn_counts(self.h, int(scan_id), _ip(cnt)))
         return cnt[:n]
+
+    COUNTER_NAMES = ("n_filtered", "n_points", "error_flags", "grid_cells", "normals_redone", "normals_per_point",
+                     "normals_blocks_handed_back", "normals_points_handed_back", "normals_trial_blocks")
+
+    def get_counters(self, scan_id):
+        """Device counters of a preprocessed scan (see arvc_scan_get_counters) as a dict."""
+        c = np.zeros(16, dtype=np.int32)
+        self._ck(self.lib.arvc_scan_get_counters(self.h, int(scan_id), _ip(c)))
+        return {k: int(v) for k, v in zip(self.COUNTER_NAMES, c)}
+
+    def set_option(self, name, value):
+        """Engine switch (arvc_ctx_set_option), e.g. ("icp_loop_graph", 0) for the unconditional max_iter + 1 enqueue."""
+        self._ck(self.lib.arvc_ctx_set_option(self.h, name.encode(), int(value)))
 
     # ---- registration
     @staticmethod
