@@ -17,7 +17,7 @@ struct NormalParams {
     int max_nn;
     int level;
     int debug;
-    int pad;
+    float crowded_ratio;                // block kernel: trial radius / radius below which a neighbourhood counts as crowded
 };
 
 struct Launcher {

@@ -703,6 +703,7 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     np.r2_hi = (float)(np.r2 * (1.0 + 2e-6));
     np.bin_scale_f = (float)np.bin_scale;
     np.debug = getenv("ARVC_DEBUG_NORMALS") ? atoi(getenv("ARVC_DEBUG_NORMALS")) : 0;
+    np.crowded_ratio = getenv("ARVC_NB_CROWDED") ? (float)atof(getenv("ARVC_NB_CROWDED")) : 1.25f;      // tuning knob; results do not depend on it
     const dim3 grid((cap_max + kNrmWarps - 1) / kNrmWarps, n_scans), block(kNrmWarps * 32);
     const size_t smem = (size_t)kNrmWarps * kWarpSmem, smem_sel = (size_t)kNrmWarps * kWarpSmemSel;
     static unsigned long long attr_set = 0;      // per device: the attribute belongs to the device's copy of the kernel

@@ -23,11 +23,20 @@ namespace arvc {
 
 namespace {
 
-constexpr int kNbWarps = 8;
+#ifndef ARVC_NBQ
+#define ARVC_NBQ 4
+#endif
+#ifndef ARVC_NBTILE
+#define ARVC_NBTILE 2048
+#endif
+#ifndef ARVC_NBWARPS
+#define ARVC_NBWARPS 8
+#endif
+constexpr int kNbWarps = ARVC_NBWARPS;
 constexpr int kNbThreads = kNbWarps * 32;
-constexpr int kNbQ = 4;                      // points per warp
+constexpr int kNbQ = ARVC_NBQ;               // points per warp
 constexpr int kNbG = kNbWarps * kNbQ;        // points per block (<= 32: one warp loads them)
-constexpr int kNbTile = 2048;                // records of the shared candidate tile
+constexpr int kNbTile = ARVC_NBTILE;         // records of the shared candidate tile
 constexpr int kNbBins = 512;
 constexpr int kNbCand = 64;                  // boundary candidates ranked exactly per point
 constexpr int kNbCells = kNbThreads;         // one cell lookup per thread and round
@@ -43,7 +52,7 @@ struct NbWarp {
 };
 
 struct NbShared {
-    float4 tile[kNbTile];
+    float4 tile[kNbTile + 64];
     float4 q[kNbG];
     uint2 runs[kNbCells];
     int roff[kNbCells + 1];
@@ -97,7 +106,10 @@ __device__ __forceinline__ int compact_runs(NbShared& S, bool valid, unsigned st
 
 }  // namespace
 
-__global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __restrict__ scans, NormalParams np) {
+#ifndef ARVC_NBOCC
+#define ARVC_NBOCC 4
+#endif
+__global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const ScanDev* __restrict__ scans, NormalParams np) {
     extern __shared__ __align__(16) unsigned char nb_smem[];
     NbShared& S = *reinterpret_cast<NbShared*>(nb_smem);
     const ScanDev& s = scans[blockIdx.y];
@@ -165,12 +177,15 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
 
     // ---- density -> trial radius.  Surface model: the U points of the looked-up cells lie on a patch of area
     // A = cl^2 * (largest face of the cell box); the ball that holds K of them has radius sqrt(K A / (pi U)).
+    // Three regimes: rt well below the radius -> search only the trial ball (`trial`); rt around the radius -> more than K
+    // points are expected inside the radius, go straight to the selection (`crowded`); else one sweep usually settles it.
     double rq = np.radius;
-    bool trial = false;
+    bool trial = false, crowded = false;
     if (U > K && L > 0) {
         const double A = cl * cl * (double)max(cnx * cny, max(cnx * cnz, cny * cnz));
         const double rt = 1.15 * sqrt((double)K * A / (3.141592653589793 * (double)U));      // 15 % safety on the model
         if (rt < 0.9 * np.radius) { trial = true; rq = rt; }
+        else if (rt < (double)np.crowded_ratio * np.radius) crowded = true;
     }
     __syncthreads();      // every thread has read roff[nruns] before the table is rebuilt
     if (trial) {
@@ -246,9 +261,13 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
         }
     }
     if (ntile > kNbTile) { __syncthreads(); block_fallback(); return; }
+    // pad to a multiple of 64 with records no ball can contain: the sweeps then run two full chunks per round
+    const int ntile_pad = (ntile + 63) & ~63;
+    if (tid < ntile_pad - ntile) S.tile[ntile + tid] = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
     __syncthreads();
     if (tid == 0) {
         if (trial) atomicAdd(&s.counts[CNT_NTRIAL_BLOCKS], 1);
+        if (np.debug & 4) { atomicAdd(&s.counts[9], ntile); atomicAdd(&s.counts[14], U); }
     }
 
     // ---- phase 4: every warp serves its points against the tile
@@ -279,17 +298,15 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
         auto exact = [&](const float4& v) -> double { return sqdist(qx, qy, qz, (double)v.x, (double)v.y, (double)v.z); };
         // everything inside the radius (decided exactly), no selection
         auto take_all = [&]() {
-            for (int j = lane; j < ntile; j += 64) {
-                const float4 a = S.tile[j];
-                const bool two = j + 32 < ntile;
-                const float4 b = S.tile[two ? j + 32 : j];
+            for (int j = lane; j < ntile_pad; j += 64) {
+                const float4 a = S.tile[j], b = S.tile[j + 32];
                 const float da = dist2f(a), db = dist2f(b);
                 if (da < rq2_lo || (da <= rq2_hi && exact(a) < rq2)) accumulate(a);
-                if (two && (db < rq2_lo || (db <= rq2_hi && exact(b) < rq2))) accumulate(b);
+                if (db < rq2_lo || (db <= rq2_hi && exact(b) < rq2)) accumulate(b);
             }
         };
         bool settled = false, failed = false;
-        if (!trial) {
+        if (!trial && !crowded) {
             // sparse / moderate neighbourhoods mostly hold <= K points inside the radius: take them all in one sweep and
             // count; only when more than K turn up is the work discarded and the selection run
             take_all();
@@ -314,12 +331,10 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
                 }
                 atomicAdd(&W.hist[b >> 1], (b & 1) ? 0x10000u : 1u);
             };
-            for (int j = lane; j < ntile; j += 64) {
-                const float4 a = S.tile[j];
-                const bool two = j + 32 < ntile;
-                const float4 b = S.tile[two ? j + 32 : j];
+            for (int j = lane; j < ntile_pad; j += 64) {
+                const float4 a = S.tile[j], b = S.tile[j + 32];
                 count_one(a);
-                if (two) count_one(b);
+                count_one(b);
             }
             __syncwarp();
             constexpr int per = kNbBins / 32;      // lane owns `per` consecutive buckets
@@ -374,12 +389,10 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
                         }
                     }
                 };
-                for (int j = lane; j < ntile; j += 64) {
-                    const float4 a = S.tile[j];
-                    const bool two = j + 32 < ntile;
-                    const float4 b = S.tile[two ? j + 32 : j];
+                for (int j = lane; j < ntile_pad; j += 64) {
+                    const float4 a = S.tile[j], b = S.tile[j + 32];
                     take_one(a, j);
-                    if (two) take_one(b, j + 32);
+                    take_one(b, j + 32);
                 }
                 __syncwarp();
                 if (bstar != kNbBins) {
@@ -409,12 +422,30 @@ __global__ void __launch_bounds__(kNbThreads, 3) k_normals_blk(const ScanDev* __
             continue;
         }
         cnt = warp_sum(cnt);
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        sxx = warp_sum(sxx); sxy = warp_sum(sxy); sxz = warp_sum(sxz);
-        syy = warp_sum(syy); syz = warp_sum(syz); szz = warp_sum(szz);
+        if ((np.debug & 4) && lane == 0) {
+            atomicAdd(&s.counts[10], cnt);
+            atomicAdd(&s.counts[(trial || crowded) ? 13 : (settled ? 11 : 12)], 1);
+        }
+        // the nine sums reduced together: every butterfly step halves the values a lane still carries (16 -> 8 -> 4 -> 2 ->
+        // 1, then one plain step), 16 double shuffles instead of 45; lane 4k ends up with sum k
+        {
+            double v[16] = {sx, sy, sz, sxx, sxy, sxz, syy, syz, szz, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int half = 8, o = 16; half >= 1; half >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                    const double mine = up ? v[k + half] : v[k], theirs = up ? v[k] : v[k + half];
+                    v[k] = mine + __shfl_xor_sync(kFull, theirs, o);
+                }
+            }
+            const double tot = v[0] + __shfl_xor_sync(kFull, v[0], 1);      // lanes 2m and 2m + 1 hold the two halves of sum idx(m)
+            // after the steps with o = 16, 8, 4, 2 lane bits 4, 3, 2, 1 select the sum: index = bit4 * 8 + bit3 * 4 + bit2 * 2 + bit1
+            const int which = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0 && which < 9) s.moments[10 * (size_t)p + which] = tot;
+        }
         if (lane == 0) {
-            double* m = s.moments + 10 * (size_t)p;
-            m[0] = sx; m[1] = sy; m[2] = sz; m[3] = sxx; m[4] = sxy; m[5] = sxz; m[6] = syy; m[7] = syz; m[8] = szz; m[9] = (double)cnt;
+            s.moments[10 * (size_t)p + 9] = (double)cnt;
             s.nn_count[p] = cnt;
         }
         __syncwarp();

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarvc_icp.so")
+LIB_PATH = os.environ.get("ARVC_LIB_VARIANT") or os.path.join(_HERE, "libarvc_icp.so")   # the variable is for developer A/B builds only
 
 P2P, P2PLANE = 0, 1
 
@@ -250,7 +250,8 @@ class Engine:
         return cnt[:n]
 
     COUNTER_NAMES = ("n_filtered", "n_points", "error_flags", "grid_cells", "normals_redone", "normals_per_point",
-                     "normals_blocks_handed_back", "normals_points_handed_back", "normals_trial_blocks")
+                     "normals_blocks_handed_back", "normals_points_handed_back", "normals_trial_blocks", "dbg_tile_records",
+                     "dbg_neighbours", "dbg_points_one_sweep", "dbg_points_sweep_then_select", "dbg_points_trial", "dbg_records_streamed")
 
     def get_counters(self, scan_id):
         """Device counters of a preprocessed scan (see arvc_scan_get_counters) as a dict."""
