@@ -160,6 +160,10 @@ typedef struct arvc_result_record {
 int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const int64_t* src_ids, const double* init_T,
                          const arvc_icp_params* p, uint64_t* ticket);
 int arvc_icp_batch_finish(arvc_ctx* ctx, uint64_t ticket, arvc_result_record* records /* [n_pairs] host */);
+/* Multi-GPU gather: device address of the pending batch's records, arvc_result_record[n_pairs], written
+ * on the context's stream when the iteration has ended and valid until arvc_icp_batch_finish(ticket).  A collective
+ * enqueued on (or ordered after) arvc_stream() can read them in place: no device -> host -> device bounce. */
+int arvc_icp_batch_device_records(arvc_ctx* ctx, uint64_t ticket, const void** d_records, int* n_pairs);
 
 /* Parity tap: one pair, recording every pass.  corr[pass*n_src + i] = target index (cloud order) matched to
  * source point i (cloud order) in that pass or -1; trace_T[pass*16..] = transformation the pass was evaluated

@@ -43,8 +43,14 @@ struct PendingBatch {
     void* slab = nullptr;
     size_t slab_bytes = 0;
     PairState* d_states = nullptr;
-    PairState* h_states = nullptr;   // pinned, from the context's pool
+    PairState* h_states = nullptr;   // pinned, from the context's pool: state heads, only read back for ARVC_DEBUG_STATS
     size_t h_bytes = 0;
+    char* h_stage = nullptr;         // pinned: [initial guesses | result records | status word]
+    size_t h_stage_bytes = 0;
+    arvc_result_record* h_records = nullptr;   // inside h_stage
+    int* h_status = nullptr;                   // inside h_stage
+    void* d_records = nullptr;       // device copy of the records (what the multi-GPU gather reads), inside the slab
+    cudaEvent_t done_ev = nullptr;   // recorded after the batch's last device->host copy
     const IcpGraph* graph = nullptr; // the device-terminated loop this batch was enqueued with (launch accounting)
 };
 
@@ -71,6 +77,13 @@ struct arvc_ctx {
     std::map<uint64_t, PendingBatch> pending;
     uint64_t next_ticket = 1;
     std::vector<std::pair<size_t, void*>> pinned_free;   // recycled pinned staging buffers
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t event_get() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        return e;
+    }
     IcpGraphCache icp_graphs;
     bool icp_use_graph = true;          // ARVC_ICP_LOOP=unrolled / arvc_ctx_set_option("icp_loop_graph", 0) switch it off
 
@@ -289,6 +302,11 @@ void arvc_ctx_destroy(arvc_ctx* ctx) {
         if (kv.second.slab) cudaFreeAsync(kv.second.slab, ctx->L.stream);
         if (kv.second.h_states) cudaFreeHost(kv.second.h_states);
     }
+    for (auto& kv : ctx->pending) {
+        if (kv.second.h_stage) cudaFreeHost(kv.second.h_stage);
+        if (kv.second.done_ev) cudaEventDestroy(kv.second.done_ev);
+    }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (auto& pf : ctx->pinned_free) cudaFreeHost(pf.second);
     for (auto& kv : ctx->scans) release_scan(ctx, kv.second.get());
     cudaStreamSynchronize(ctx->copy_stream);
@@ -418,6 +436,9 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         todo.push_back(s);
     }
     if (todo.empty()) return ARVC_OK;
+    // from here on a failure leaves these scans without usable device state: they count as not preprocessed until the
+    // publish loop at the end marks them again (an early return must never leave `preprocessed` set over freed buffers)
+    for (Scan* s : todo) { s->preprocessed = false; s->has_normals = false; }
     for (Scan* s : todo) await_upload(ctx, s);
 
     // ---- allocate: persistent slab per scan, one scratch slab for the batch
@@ -771,6 +792,9 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
         PairDev* d_pairs = P.take<PairDev>(n_pairs);
         PairState* d_states = P.take<PairState>(n_pairs);
         BatchDesc* d_bd = P.take<BatchDesc>(1);
+        double* d_init = P.take<double>(16 * (size_t)n_pairs);
+        arvc_result_record* d_records = P.take<arvc_result_record>(n_pairs);
+        int* d_status = P.take<int>(4);
         std::vector<PairDev> hp(pass ? n_pairs : 0);
         for (int i = 0; i < n_pairs; ++i) {
             const size_t cap = (size_t)S[i]->dev.cap;
@@ -780,11 +804,12 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             float* lb2 = P.take<float>(cap);
             unsigned char* cpass = P.take<unsigned char>(cap);
             int* list = P.take<int>(cap + (cap + 255) / 256 * 32);   // + padding per block of the select kernel
+            int* far_list = P.take<int>(cap);
             int* ct = trace ? P.take<int>(cap * passes) : nullptr;
             double* stt = trace ? P.take<double>((size_t)passes * 18) : nullptr;
             if (pass) {
                 hp[i].src = S[i]->d_dev; hp[i].tgt = T[i]->d_dev; hp[i].state = d_states + i;
-                hp[i].partials = partials; hp[i].prev = prev; hp[i].lb2 = lb2; hp[i].cert_pass = cpass; hp[i].list = list; hp[i].corr_trace = ct; hp[i].state_trace = stt;
+                hp[i].partials = partials; hp[i].prev = prev; hp[i].lb2 = lb2; hp[i].cert_pass = cpass; hp[i].list = list; hp[i].far_list = far_list; hp[i].corr_trace = ct; hp[i].state_trace = stt;
                 if (trace && d_corr_trace) { *d_corr_trace = ct; *d_state_trace = stt; }
             }
         }
@@ -795,15 +820,18 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
             if (trace) CK(cudaMemsetAsync(pb.slab, 0xff, plan.off, ctx->L.stream));   // untouched trace entries read as -1 / NaN
         } else {
             pb.d_states = d_states;
-            pb.h_states = reinterpret_cast<PairState*>(ctx->pinned_get(sizeof(PairState) * n_pairs, &pb.h_bytes));
-            if (!pb.h_states) return ctx->fail(ARVC_E_NOMEM, "icp: pinned host allocation failed");
-            std::memset(pb.h_states, 0, sizeof(PairState) * n_pairs);
-            for (int i = 0; i < n_pairs; ++i) {
-                std::memcpy(pb.h_states[i].T, init_T + 16 * (size_t)i, sizeof(double) * 16);
-                std::memcpy(pb.h_states[i].Thist, init_T + 16 * (size_t)i, sizeof(double) * 12);
-            }
+            pb.d_records = d_records;
+            const bool debug_stats = getenv("ARVC_DEBUG_STATS") != nullptr;
+            const size_t init_bytes = sizeof(double) * 16 * (size_t)n_pairs, rec_bytes = sizeof(arvc_result_record) * (size_t)n_pairs;
+            pb.h_stage = reinterpret_cast<char*>(ctx->pinned_get(init_bytes + rec_bytes + 16, &pb.h_stage_bytes));
+            if (debug_stats) pb.h_states = reinterpret_cast<PairState*>(ctx->pinned_get(sizeof(PairState) * n_pairs, &pb.h_bytes));
+            if (!pb.h_stage || (debug_stats && !pb.h_states)) return ctx->fail(ARVC_E_NOMEM, "icp: pinned host allocation failed");
+            pb.h_records = reinterpret_cast<arvc_result_record*>(pb.h_stage + init_bytes);
+            pb.h_status = reinterpret_cast<int*>(pb.h_stage + init_bytes + rec_bytes);
+            std::memcpy(pb.h_stage, init_T, init_bytes);
             CK(cudaMemcpyAsync(d_pairs, hp.data(), sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
-            CK(cudaMemcpyAsync(d_states, pb.h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->L.stream));
+            CK(cudaMemcpyAsync(d_init, pb.h_stage, init_bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+            launch_icp_init(ctx->L, d_pairs, n_pairs, d_init, d_status);
             BatchDesc bd{};
             bd.pairs = d_pairs; bd.n_pairs = n_pairs;
             IcpParams& ip = bd.ip;
@@ -816,9 +844,15 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
                 ip.debug = getenv("ARVC_DEBUG_STATS") ? atoi(getenv("ARVC_DEBUG_STATS")) : 0;
             }
             pb.graph = run_icp(ctx->L, ctx->icp_graphs, bd, d_bd, src_cap_max, combos, ctx->icp_use_graph);
+            launch_icp_pack(ctx->L, d_pairs, n_pairs, d_records, d_status);
+            CK(cudaMemcpyAsync(pb.h_records, d_records, rec_bytes, cudaMemcpyDeviceToHost, ctx->L.stream));
+            CK(cudaMemcpyAsync(pb.h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
             static_assert(offsetof(PairState, Thist) == kPairStateHead, "PairState head layout");
-            CK(cudaMemcpy2DAsync(pb.h_states, sizeof(PairState), d_states, sizeof(PairState), kPairStateHead, n_pairs,
-                                 cudaMemcpyDeviceToHost, ctx->L.stream));
+            if (debug_stats)
+                CK(cudaMemcpy2DAsync(pb.h_states, sizeof(PairState), d_states, sizeof(PairState), kPairStateHead, n_pairs,
+                                     cudaMemcpyDeviceToHost, ctx->L.stream));
+            pb.done_ev = ctx->event_get();
+            CK(cudaEventRecord(pb.done_ev, ctx->L.stream));
         }
     }
     if (src_cap_out) *src_cap_out = src_cap_max;
@@ -826,13 +860,22 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
     return ARVC_OK;
 }
 
-static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec) {
-    CK(cudaStreamSynchronize(ctx->L.stream));
+static void icp_release(arvc_ctx* ctx, PendingBatch& pb) {
     if (pb.slab) { ctx->dev_put(pb.slab, pb.slab_bytes); pb.slab = nullptr; }
-    struct Recycle { arvc_ctx* c; PendingBatch& b; ~Recycle() { c->pinned_put(b.h_states, b.h_bytes); b.h_states = nullptr; } } recycle{ctx, pb};
+    ctx->pinned_put(pb.h_states, pb.h_bytes); pb.h_states = nullptr;
+    ctx->pinned_put(pb.h_stage, pb.h_stage_bytes); pb.h_stage = nullptr;
+    if (pb.done_ev) { ctx->event_pool.push_back(pb.done_ev); pb.done_ev = nullptr; }
+}
+
+// Waits for THIS batch only (its own event): batches enqueued later keep running, which is what lets a caller overlap the
+// delivery of batch k with the kernels of batch k + 1.
+static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec) {
+    if (pb.n_pairs == 0) return ARVC_OK;
+    const cudaError_t werr = pb.done_ev ? cudaEventSynchronize(pb.done_ev) : cudaStreamSynchronize(ctx->L.stream);
+    struct Release { arvc_ctx* c; PendingBatch& b; ~Release() { icp_release(c, b); } } release{ctx, pb};
+    if (werr != cudaSuccess) return ctx->cuda_fail(werr, "icp: waiting for the batch");
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
-    int err = 0;
-    if (getenv("ARVC_DEBUG_STATS")) {
+    if (pb.h_states) {      // ARVC_DEBUG_STATS
         unsigned long long tot[8] = {0};
         long long passes = 0;
         for (int i = 0; i < pb.n_pairs; ++i) { for (int k = 0; k < 8; ++k) tot[k] += pb.h_states[i].dbg[k]; passes += pb.h_states[i].passes; }
@@ -847,21 +890,14 @@ static int icp_collect(arvc_ctx* ctx, PendingBatch& pb, arvc_result_record* rec)
     }
     if (pb.graph) {      // kernels the device-terminated loop executed: the prefix + one body per pass beyond it
         int max_passes = 0;
-        for (int i = 0; i < pb.n_pairs; ++i) max_passes = std::max(max_passes, pb.h_states[i].passes);
+        for (int i = 0; i < pb.n_pairs; ++i) max_passes = std::max(max_passes, (int)pb.h_records[i].passes);
         ctx->L.launches += pb.graph->kernels_prefix + (long long)pb.graph->kernels_body * std::max(0, max_passes - kIcpUnrolled);
     }
-    for (int i = 0; i < pb.n_pairs; ++i) {
-        const PairState& st = pb.h_states[i];
-        err |= st.err;
-        if (!st.done) return ctx->fail(ARVC_E_CUDA, "icp: a pair did not terminate (internal error)");
-        if (rec) {
-            rec[i].pair = i; rec[i].updates = st.updates; rec[i].n_corr = st.ncorr; rec[i].passes = st.passes;
-            std::memcpy(rec[i].T, st.T, sizeof(double) * 16);
-            rec[i].fitness = st.fitness; rec[i].rmse = st.rmse;
-        }
-    }
-    if (err & ERR_HASH_FULL) return ctx->fail(ARVC_E_CAPACITY, "hash grid overflow in a scan of this batch");
-    if (err & ERR_VOXEL_RANGE) return ctx->fail(ARVC_E_CAPACITY, "voxel index outside the range implied by the filter bounds");
+    const int flags = *pb.h_status;
+    if (flags & 0x100) return ctx->fail(ARVC_E_CUDA, "icp: a pair did not terminate (internal error)");
+    if (rec) std::memcpy(rec, pb.h_records, sizeof(arvc_result_record) * (size_t)pb.n_pairs);
+    if (flags & ERR_HASH_FULL) return ctx->fail(ARVC_E_CAPACITY, "hash grid overflow in a scan of this batch");
+    if (flags & ERR_VOXEL_RANGE) return ctx->fail(ARVC_E_CAPACITY, "voxel index outside the range implied by the filter bounds");
     return ARVC_OK;
 }
 
@@ -870,9 +906,18 @@ int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, con
     if (!ctx || !ticket) return ARVC_E_ARG;
     PendingBatch pb;
     const int rc = icp_enqueue(ctx, n_pairs, tgt_ids, src_ids, init_T, p, false, pb, nullptr, nullptr, nullptr);
-    if (rc) { ctx->dev_put(pb.slab, pb.slab_bytes); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    if (rc) { icp_release(ctx, pb); return rc; }
     *ticket = ctx->next_ticket++;
     ctx->pending[*ticket] = std::move(pb);
+    return ARVC_OK;
+}
+
+int arvc_icp_batch_device_records(arvc_ctx* ctx, uint64_t ticket, const void** d_records, int* n_pairs) {
+    if (!ctx || !d_records) return ARVC_E_ARG;
+    auto it = ctx->pending.find(ticket);
+    if (it == ctx->pending.end()) return ctx->fail(ARVC_E_ARG, "icp_batch_device_records: unknown ticket");
+    *d_records = it->second.d_records;
+    if (n_pairs) *n_pairs = it->second.n_pairs;
     return ARVC_OK;
 }
 
@@ -912,12 +957,13 @@ int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* 
     double* d_st = nullptr;
     int cap = 0;
     int rc = icp_enqueue(ctx, 1, &tgt_id, &src_id, init_T, p, true, pb, &d_ct, &d_st, &cap);
-    if (rc) { ctx->dev_put(pb.slab, pb.slab_bytes); ctx->pinned_put(pb.h_states, pb.h_bytes); return rc; }
+    if (rc) { icp_release(ctx, pb); return rc; }
     const int passes_max = p->max_iter + 1;
     std::vector<int> hct((size_t)cap * passes_max);
     std::vector<double> hst((size_t)passes_max * 18);
     CK(cudaMemcpyAsync(hct.data(), d_ct, sizeof(int) * hct.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
     CK(cudaMemcpyAsync(hst.data(), d_st, sizeof(double) * hst.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));      // the trace copies are queued behind the batch's own completion event
     arvc_result_record rec;
     rc = icp_collect(ctx, pb, &rec);
     if (rc) return rc;

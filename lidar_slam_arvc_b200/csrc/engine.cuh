@@ -77,7 +77,8 @@ struct __align__(16) PairState {
     int ncorr;
     int err;                // OR of the two scans' device error flags
     int nlist;              // entries of the work list of the current pass
-    int pad[2];
+    int nfar;               // entries of the far list of the current pass
+    int pad[1];
     unsigned long long dbg[8];   // search statistics (ARVC_DEBUG_STATS): skipped / union / fallback queries, queries, fallback by level
     // ---- device-only tail (not copied back): top three rows of the transformation each pass was evaluated at
     double Thist[12 * kThist];
@@ -93,6 +94,7 @@ struct PairDev {
     float* lb2;             // [src cap] certificate: lower bound on the distance to every other target point ...
     unsigned char* cert_pass;   // [src cap] ... at the pass it was established (255 = none)
     int* list;              // [src cap] source points whose nearest neighbour has to be searched in this pass
+    int* far_list;          // [src cap] of those, the ones the shared-candidate phase could not settle: point | start level << 24
     int* corr_trace;        // optional [(max_iter+1)][src cap] (cloud order), may be null
     double* state_trace;    // optional [(max_iter+1)][18]: T16, fitness, rmse
 };
@@ -145,6 +147,8 @@ void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int ca
 const IcpGraph* run_icp(Launcher& L, IcpGraphCache& cache, const BatchDesc& h_bd, BatchDesc* d_bd_batch, int src_cap_max, int combos_mask,
                         bool use_graph);
 void icp_graphs_destroy(IcpGraphCache& cache);
+void launch_icp_init(Launcher& L, const PairDev* d_pairs, int n_pairs, const double* d_init, int* d_status);
+void launch_icp_pack(Launcher& L, const PairDev* d_pairs, int n_pairs, void* d_records, int* d_status);
 void run_plane_fit(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_score, double* d_result, double max_z, double thr,
                    int iters, unsigned long long seed);
 void run_plane_split(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_blk, double* d_near, double* d_far, int* d_counts2,

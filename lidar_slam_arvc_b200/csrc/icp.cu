@@ -46,6 +46,7 @@ constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may 
 constexpr int kUnionScanCap = 384;    // larger unions are split per query (lanes share the records of one query)
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
+constexpr int kFarBlocks = 296;   // blocks per pair of the far-query kernel (2 x 148 SMs)
 
 __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
     const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
@@ -427,8 +428,7 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
     __shared__ int s_spos[kGroupsPerBlock][kStage];
-    __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
-    __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
+    __shared__ uint4 s_stk[kGroupsPerBlock][kStack];      // the union phase's run table
 
     if ((int)blockIdx.y >= bd->n_pairs) return;
     const PairDev& pr = bd->pairs[blockIdx.y];
@@ -685,34 +685,17 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
         }
     }
     const long long t_union_end = clock64();
-    // ---- remaining queries (nearest neighbour beyond the union levels): the warp's pending queries are dealt round
-    // robin to its 32/kG groups, each group serving one query at a time with the cooperative branch-and-bound search
+    // ---- remaining queries (nearest neighbour beyond the union levels): handed to k_icp_far through the pair's far
+    // list, one entry per query, so that they spread over the whole GPU instead of queueing inside this warp.  The
+    // bound travels implicitly: prev[i] (written below) holds the best match so far, k_icp_far re-derives its distance.
     {
-        const unsigned pend = __ballot_sync(kFull, active && !certified && !(ip.debug & 2));
-        const int npend = __popc(pend);
-        constexpr int kGroupsPerWarp = 32 / kG;
-        const int wg = lane / kG;                      // group index inside the warp
-        for (int base = 0; base < npend; base += kGroupsPerWarp) {
-            const int item = base + wg;                // the item-th pending lane of the warp (ascending lane order)
-            int owner = -1;
-            if (item < npend) owner = __fns(pend, 0, item + 1);
-            const int src_lane = owner >= 0 ? owner : 0;
-            const double qx = __shfl_sync(kFull, sx, src_lane), qy = __shfl_sync(kFull, sy, src_lane), qz = __shfl_sync(kFull, sz, src_lane);
-            const double qd2 = __shfl_sync(kFull, b.d2, src_lane);
-            const int qidx = __shfl_sync(kFull, b.idx, src_lane), ql = __shfl_sync(kFull, level, src_lane);
-            Best lb;
-            lb.d2 = 0; lb.idx = 0; lb.pos = -1;
-            if (owner >= 0) group_search<TW>(tgt, qx, qy, qz, qd2, qidx, ql, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
-            // hand the results back: the lane that owns item j reads them from group j % kGroupsPerWarp
-            const int my_item = (active && !certified) ? __popc(pend & ((1u << lane) - 1u)) : -1;
-            const bool mine = my_item >= base && my_item < base + kGroupsPerWarp;
-            const int from = mine ? (my_item - base) * kG : 0;
-            const double rd2 = __shfl_sync(kFull, lb.d2, from);
-            const int ridx = __shfl_sync(kFull, lb.idx, from), rpos = __shfl_sync(kFull, lb.pos, from);
-            if (mine) {
-                if (rpos >= 0) { b.d2 = rd2; b.idx = ridx; b.pos = rpos; }
-                ++stat_fb;
-            }
+        const bool pending = active && !certified && !(ip.debug & 2);
+        const unsigned pend = __ballot_sync(kFull, pending);
+        if (pend) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&pr.state->nfar, __popc(pend));
+            base = __shfl_sync(kFull, base, 0);
+            if (pending) { pr.far_list[base + __popc(pend & ((1u << lane) - 1u))] = i | (level << 24); ++stat_fb; }
         }
     }
 
@@ -737,6 +720,56 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
     }
     __syncwarp();
     }   // chunk loop
+}
+
+// Far queries of a pass (their nearest neighbour lies beyond the cells the shared-candidate phase covers): one 8-lane
+// group per far-list entry, cooperative branch and bound over the coarser levels, groups striding over the list.
+template <bool SW, bool TW>
+__global__ void __launch_bounds__(kIcpBlock) k_icp_far(const BatchDesc* __restrict__ bd) {
+    typedef typename RecT<SW>::type SRec;
+    typedef typename RecT<TW>::type TRec;
+    __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
+    __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
+    if ((int)blockIdx.y >= bd->n_pairs) return;
+    const PairDev& pr = bd->pairs[blockIdx.y];
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
+    const PairState* __restrict__ st = pr.state;
+    if (st->done) return;
+    const int nfar = st->nfar;
+    const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
+    const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
+    const double max_d2 = bd->ip.max_d2;
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
+#pragma unroll 1
+    for (int f = blockIdx.x * kGroupsPerBlock + grp; f < nfar; f += gridDim.x * kGroupsPerBlock) {
+        const int e = pr.far_list[f];
+        const int i = e & 0xffffff, level = e >> 24;
+        double px, py, pz;
+        int sidx;
+        load_rec(reinterpret_cast<const SRec*>(src.recs) + i, px, py, pz, sidx);
+        const double sx = T[0] * px + T[1] * py + T[2] * pz + T[3];
+        const double sy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+        const double sz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+        // the bound: best match so far (previous pass' match or what the shared-candidate phase found), else the cut-off
+        double bd2 = max_d2;
+        int bidx = -1;
+        const int pv = pr.prev[i];
+        if (pv >= 0) {
+            double x, y, z;
+            int idx;
+            load_rec(reinterpret_cast<const TRec*>(tgt.recs) + pv, x, y, z, idx);
+            const double d2 = sqdist(sx, sy, sz, x, y, z);
+            if (d2 < bd2) { bd2 = d2; bidx = idx; }
+        }
+        Best lb;
+        group_search<TW>(tgt, sx, sy, sz, bd2, bidx, level, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
+        if (gl == 0 && lb.pos >= 0) pr.prev[i] = lb.pos;      // else: nothing strictly better than the bound, prev[i] stands
+        __syncwarp(gmask);
+    }
 }
 
 constexpr int kAccPts = 4;                                  // source points per lane of the accumulation kernel
@@ -874,6 +907,7 @@ __global__ void __launch_bounds__(256) k_icp_finish(const BatchDesc* __restrict_
         for (int k = 0; k < kNS; ++k) st->sums[k] = s_sum[k];
         if (ip.debug & 1) st->dbg[3] += (unsigned long long)n;
         st->nlist = 0;
+        st->nfar = 0;
         if (stop) {
             st->done = 1;
         } else {
@@ -886,6 +920,44 @@ __global__ void __launch_bounds__(256) k_icp_finish(const BatchDesc* __restrict_
         }
         st->err = src.counts[CNT_ERR] | tgt.counts[CNT_ERR];
     }
+}
+
+// Batch set-up and delivery, one thread per pair: the pair states are initialised on the device from the compact array
+// of initial guesses (128 B per pair instead of the whole state), and the results leave as 160-byte records - the unit
+// the multi-GPU gather moves - plus one status word (error flags of the scans, 0x100 = a pair did not terminate).
+__global__ void __launch_bounds__(128) k_icp_init(const PairDev* __restrict__ pairs, int n_pairs, const double* __restrict__ init_T, int* __restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *status = 0;
+    if (i >= n_pairs) return;
+    PairState* st = pairs[i].state;
+    for (int k = 0; k < 16; ++k) st->T[k] = init_T[16 * (size_t)i + k];
+    for (int k = 0; k < 12; ++k) st->Thist[k] = init_T[16 * (size_t)i + k];
+    st->fitness = 0.0; st->rmse = 0.0;
+    st->passes = 0; st->updates = 0; st->done = 0; st->ncorr = 0; st->err = 0; st->nlist = 0; st->nfar = 0;
+    for (int k = 0; k < 8; ++k) st->dbg[k] = 0ull;
+}
+
+struct __align__(8) ResultRecordDev { int pair, updates, n_corr, passes; double T[16]; double fitness, rmse; };
+static_assert(sizeof(ResultRecordDev) == 160, "result records are 160 bytes (include/arvc_icp.h)");
+
+__global__ void __launch_bounds__(128) k_icp_pack(const PairDev* __restrict__ pairs, int n_pairs, ResultRecordDev* __restrict__ out, int* __restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const PairState* st = pairs[i].state;
+    ResultRecordDev r;
+    r.pair = i; r.updates = st->updates; r.n_corr = st->ncorr; r.passes = st->passes;
+    for (int k = 0; k < 16; ++k) r.T[k] = st->T[k];
+    r.fitness = st->fitness; r.rmse = st->rmse;
+    out[i] = r;
+    const int flags = st->err | (st->done ? 0 : 0x100);
+    if (flags) atomicOr(status, flags);
+}
+
+void launch_icp_init(Launcher& L, const PairDev* d_pairs, int n_pairs, const double* d_init, int* d_status) {
+    L.launch("icp_init", k_icp_init, dim3((n_pairs + 127) / 128), dim3(128), d_pairs, n_pairs, d_init, d_status);
+}
+void launch_icp_pack(Launcher& L, const PairDev* d_pairs, int n_pairs, void* d_records, int* d_status) {
+    L.launch("icp_pack", k_icp_pack, dim3((n_pairs + 127) / 128), dim3(128), d_pairs, n_pairs, reinterpret_cast<ResultRecordDev*>(d_records), d_status);
 }
 
 // WHILE condition of the device-terminated loop: non-zero while some pair of the batch has not converged.
@@ -948,6 +1020,12 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     if (combos_mask & 2) E.kernel(nm, (const void*)k_icp_search<false, true>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
+    // far queries: a few per cent of the points; 296 blocks x 8 groups per pair stride over the pair's far list
+    const dim3 gfar(kFarBlocks, n_pairs_grid);
+    if (combos_mask & 1) E.kernel("icp_far", (const void*)k_icp_far<false, false>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel("icp_far", (const void*)k_icp_far<false, true>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel("icp_far", (const void*)k_icp_far<true, false>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel("icp_far", (const void*)k_icp_far<true, true>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 1) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), args);

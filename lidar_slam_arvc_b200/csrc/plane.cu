@@ -1,8 +1,11 @@
 // Ground-plane model and split for the reference's 'icp2planes' method:
 //   KeyFrame.calculate_plane (keyframe.py:417-436): plane through the points below a height, Open3D segment_plane
-//     (RANSAC, 3-point hypotheses, 1000 iterations, unseeded).  Here: the same hypothesis test, but the samples come
+//     (RANSAC, 3-point hypotheses, 1000 iterations, unseeded) followed by its least-squares refit of the plane to
+//     the inliers of the winning hypothesis.  Here: the same hypothesis test and the same refit, but the samples come
 //     from a counter-based hash of (seed, iteration), so the result is reproducible and the CPU oracle repeats it bit
-//     for bit.  One block per hypothesis counts its inliers; a second kernel keeps the best (lowest iteration on ties).
+//     for bit.  One block per hypothesis counts its inliers; a second kernel keeps the best one; a third refits.
+//     Stated differences: hypotheses with equal inlier counts are ranked by iteration (lowest wins) where Open3D takes
+//     the lower inlier RMSE, and all `iterations` hypotheses are evaluated (Open3D may stop early at probability 1).
 //   KeyFrame.segment_plane (keyframe.py:438-461): |a x + b y + c z + d| / sqrt(a^2+b^2+c^2) < threshold splits the
 //     cloud, order preserved - a stable two-way compaction into the raw buffers of two new scans.
 // Both work on the preprocessed cloud in the reference's point order, which is first restored from the Morton-sorted
@@ -110,11 +113,70 @@ __global__ void __launch_bounds__(1024) k_plane_pick(const ScanDev* __restrict__
     }
 }
 
+// Open3D's segment_plane does not return the winning 3-point hypothesis: it collects the final inliers of that
+// hypothesis (|plane . (x, y, z, 1)| < threshold) and refits the plane to ALL of them (GetPlaneFromPoints: centroid,
+// centred second moments, normal = the largest of the three 2x2-determinant cross products, normalised; d = -n.c).
+// Fixed summation order so that the oracle repeats it bit for bit: thread t of 1024 sums the inliers i = t, t + 1024, ...
+// in ascending order, then xor-butterfly inside every warp (16, 8, 4, 2, 1), then the same butterfly over the 32 warp sums.
+__device__ __forceinline__ double block1024_sum(double v, double* s_w /*[32]*/) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = s_w[lane_id()];
+    t = warp_sum(t);
+    return t;      // every thread returns the same value
+}
+
+__global__ void __launch_bounds__(1024) k_plane_refit(const ScanDev* __restrict__ sp, const double* __restrict__ pts, double max_z, double thr,
+                                                      double* __restrict__ result) {
+    __shared__ double s_w[32];
+    const int n = sp->counts[CNT_NPTS];
+    const double pl[4] = {result[0], result[1], result[2], result[3]};
+    if (!(result[4] >= 3.0)) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+        if (z < max_z && fabs(plane_value(pl, x, y, z)) < thr) { sx = __dadd_rn(sx, x); sy = __dadd_rn(sy, y); sz = __dadd_rn(sz, z); cnt += 1.0; }
+    }
+    sx = block1024_sum(sx, s_w); sy = block1024_sum(sy, s_w); sz = block1024_sum(sz, s_w); cnt = block1024_sum(cnt, s_w);
+    const double cx = __ddiv_rn(sx, cnt), cy = __ddiv_rn(sy, cnt), cz = __ddiv_rn(sz, cnt);
+    double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+        if (z < max_z && fabs(plane_value(pl, x, y, z)) < thr) {
+            const double r0 = __dsub_rn(x, cx), r1 = __dsub_rn(y, cy), r2 = __dsub_rn(z, cz);
+            xx = __dadd_rn(xx, __dmul_rn(r0, r0)); xy = __dadd_rn(xy, __dmul_rn(r0, r1)); xz = __dadd_rn(xz, __dmul_rn(r0, r2));
+            yy = __dadd_rn(yy, __dmul_rn(r1, r1)); yz = __dadd_rn(yz, __dmul_rn(r1, r2)); zz = __dadd_rn(zz, __dmul_rn(r2, r2));
+        }
+    }
+    xx = block1024_sum(xx, s_w); xy = block1024_sum(xy, s_w); xz = block1024_sum(xz, s_w);
+    yy = block1024_sum(yy, s_w); yz = block1024_sum(yz, s_w); zz = block1024_sum(zz, s_w);
+    if (threadIdx.x != 0) return;
+    const double det_x = __dsub_rn(__dmul_rn(yy, zz), __dmul_rn(yz, yz));
+    const double det_y = __dsub_rn(__dmul_rn(xx, zz), __dmul_rn(xz, xz));
+    const double det_z = __dsub_rn(__dmul_rn(xx, yy), __dmul_rn(xy, xy));
+    double a, b, c;
+    if (det_x > det_y && det_x > det_z) {
+        a = det_x; b = __dsub_rn(__dmul_rn(xz, yz), __dmul_rn(xy, zz)); c = __dsub_rn(__dmul_rn(xy, yz), __dmul_rn(xz, yy));
+    } else if (det_y > det_z) {
+        a = __dsub_rn(__dmul_rn(xz, yz), __dmul_rn(xy, zz)); b = det_y; c = __dsub_rn(__dmul_rn(xy, xz), __dmul_rn(yz, xx));
+    } else {
+        a = __dsub_rn(__dmul_rn(xy, yz), __dmul_rn(xz, yy)); b = __dsub_rn(__dmul_rn(xy, xz), __dmul_rn(yz, xx)); c = det_z;
+    }
+    const double norm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+    if (norm == 0.0) { result[0] = result[1] = result[2] = result[3] = 0.0; result[4] = 0.0; return; }      // the inliers do not span a plane
+    a = __ddiv_rn(a, norm); b = __ddiv_rn(b, norm); c = __ddiv_rn(c, norm);
+    result[0] = a; result[1] = b; result[2] = c;
+    result[3] = -__dadd_rn(__dadd_rn(__dmul_rn(a, cx), __dmul_rn(b, cy)), __dmul_rn(c, cz));
+}
+
 void run_plane_fit(Launcher& L, const ScanDev* d_scan, int cap, double* d_orig, int* d_score, double* d_result, double max_z, double thr,
                    int iters, unsigned long long seed) {
     L.launch("plane_unpermute", k_plane_unpermute, dim3(max(1, min((cap + 255) / 256, 592))), dim3(256), d_scan, d_orig);
     L.launch("plane_ransac", k_plane_ransac, dim3(iters), dim3(256), d_scan, (const double*)d_orig, max_z, thr, seed, d_score);
     L.launch("plane_pick", k_plane_pick, dim3(1), dim3(1024), d_scan, (const double*)d_orig, max_z, seed, (const int*)d_score, iters, d_result);
+    L.launch("plane_refit", k_plane_refit, dim3(1), dim3(1024), d_scan, (const double*)d_orig, max_z, thr, d_result);
 }
 
 // ---- split --------------------------------------------------------------------------------------------

@@ -7,8 +7,10 @@ path uses (`icppointpoint`, `icppointplane`); the Open3D calls are replaced by c
     pre_process / preprocess_* keyframe.py:113-162   ) arvc_scan_preprocess
     local_registration_simple  keyframe.py:231-260   arvc_icp_batch (one pair)
     unload_pointcloud          keyframe.py:61-72     arvc_scan_free
-The reference's `icp2planes` and `fpfh` methods depend on Open3D's unseeded RANSAC and are out of scope
-(SURVEY.md §2 #17): they raise NotImplementedError instead of silently doing something else.
+    preprocess_icp2planes / calculate_plane / segment_plane / local_registration_two_planes
+                               keyframe.py:164-189, 417-461, 262-295   arvc_scan_fit_plane / _split_plane + one batch of two pairs
+The reference's `fpfh` method (Open3D feature matching + RANSAC global registration) is out of scope:
+it raises NotImplementedError instead of silently doing something else.
 """
 import numpy as np
 
@@ -65,7 +67,8 @@ class KeyFrame():
         self.min_radius = ICP_PARAMETERS.min_radius
         self.max_height = ICP_PARAMETERS.max_height
         self.min_height = ICP_PARAMETERS.min_height
-        self.plane_model = None
+        self.plane_model = None                  # the ground plane of the last icp2planes preprocessing (keyframe.py:173)
+        self.fixed_plane_model = None            # extension: a caller-supplied model (cf. the fixed [0, 0, 1, 0.69] of keyframe.py:436)
         self.pre_processed = False               # never set by the reference either (keyframe.py:39,114)
         self.last_result = None                  # extension: fitness / inlier_rmse / iterations of the last registration
         self._scan_id = runtime.new_scan_id()
@@ -199,10 +202,10 @@ class KeyFrame():
     def preprocess_icp2planes(self):
         """keyframe.py:164-189: filter -> [voxel] -> normals, ground-plane model, split into the points within 0.4 m of
         the plane and the rest, normals of both parts (radius 0.5 / max_nn_gd on the ground, 0.3 / max_nn elsewhere).
-        A plane_model assigned by the caller beforehand is kept (the reference hints at a fixed model, keyframe.py:436)."""
+        Like the reference, the plane is recomputed on every call (keyframe.py:173) - unless the caller pinned one in
+        `fixed_plane_model` (the reference hints at a fixed model, keyframe.py:436)."""
         self._preprocess(self._params(True))
-        if self.plane_model is None:
-            self.plane_model = self.calculate_plane()
+        self.plane_model = np.asarray(self.fixed_plane_model, dtype=np.float64) if self.fixed_plane_model is not None else self.calculate_plane()
         self.segment_plane(self.plane_model, _download=False)
         eng = runtime.get_engine()
         for sid, radius, max_nn in ((self._scan_id_ground, self.voxel_size_normals_ground_plane, ICP_PARAMETERS.max_nn_gd),

@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
     "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane", "arvc_ctx_set_option", "arvc_scan_get_counters",
+    "arvc_icp_batch_device_records",
 ]
 
 
@@ -83,6 +84,7 @@ def load_library():
     lib.arvc_icp_batch.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), dp, dp, dp, ip, ip]
     lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
     lib.arvc_icp_batch_finish.argtypes = [vp, c.c_uint64, vp]
+    lib.arvc_icp_batch_device_records.argtypes = [vp, c.c_uint64, c.POINTER(vp), ip]
     lib.arvc_icp_trace.argtypes = [vp, c.c_int64, c.c_int64, dp, c.POINTER(IcpParams), ip, dp, dp, dp, ip, c.POINTER(ResultRecord)]
     lib.arvc_map_build.argtypes = [vp, c.c_int, i64p, dp, c.POINTER(PreprocessParams), dp, c.c_int64, i64p]
     lib.arvc_scan_fit_plane.argtypes = [vp, c.c_int64, c.c_double, c.c_double, c.c_int, c.c_uint64, dp, ip]
@@ -276,6 +278,13 @@ class Engine:
         ticket = ctypes.c_uint64()
         self._ck(self.lib.arvc_icp_batch_async(self.h, len(t), _i64p(t), _i64p(s), _dp(T), ctypes.byref(params), ctypes.byref(ticket)))
         return ticket.value, len(t)
+
+    def icp_batch_device_records(self, ticket):
+        """(device address, n_pairs) of a pending batch's 160-byte records; valid until icp_batch_finish(ticket)."""
+        tk, n = ticket
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_int32()
+        self._ck(self.lib.arvc_icp_batch_device_records(self.h, ctypes.c_uint64(tk), ctypes.byref(ptr), ctypes.byref(cnt)))
+        return ptr.value or 0, cnt.value
 
     def icp_batch_finish(self, ticket):
         tk, n = ticket

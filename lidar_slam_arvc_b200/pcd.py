@@ -35,14 +35,19 @@ def read_pcd_xyz(filename):
         n = int(header["POINTS"][0]) if "POINTS" in header else int(header["WIDTH"][0]) * int(header["HEIGHT"][0])
         data = header["DATA"][0].lower()
         names, formats = [], []
-        for fld, sz, tp, cnt in zip(fields, sizes, types, counts):
-            dt = _NP[(tp.upper(), sz)]
+        for pos, (fld, sz, tp, cnt) in enumerate(zip(fields, sizes, types, counts)):
+            dt = _NP.get((tp.upper(), sz))
+            if dt is None:
+                raise ValueError("%s: unsupported PCD field type %s of size %d (field %s)" % (filename, tp, sz, fld))
+            # PCL writes padding as repeated fields named "_" (e.g. "x y z _ intensity _"): everything but x / y / z gets its
+            # position appended, so that the record dtype never sees a duplicate name
+            base = fld if fld in ("x", "y", "z") and fld not in names else "%s@%d" % (fld, pos)
             if cnt == 1:
-                names.append(fld)
+                names.append(base)
                 formats.append(dt)
             else:
                 for c in range(cnt):
-                    names.append("%s_%d" % (fld, c))
+                    names.append("%s_%d" % (base, c))
                     formats.append(dt)
         if data == "binary":
             rec = np.dtype({"names": names, "formats": formats})

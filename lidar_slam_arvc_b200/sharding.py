@@ -59,3 +59,64 @@ def gather_records(records, device=None, group=None, counts=None):
     host = out.cpu().numpy().reshape(world, cap, words)
     parts = [host[r, :counts[r]].reshape(-1).view(RESULT_DTYPE) for r in range(world)]
     return np.concatenate(parts) if parts else records
+
+
+class _DeviceBytes:
+    """A raw device allocation owned by the engine, exposed through __cuda_array_interface__ so that torch can wrap it
+    without a copy (plumbing only: torch.distributed needs a tensor to hand to NCCL)."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<f8", "data": (int(ptr), True), "version": 3}
+
+
+class DeviceGather:
+    """All-gather of the 160-byte result records straight from the engine's device memory.
+
+    `start(ticket)` is called right after `icp_batch_async`: on the engine's own stream - i.e. ordered after the last
+    kernel of the batch, with no host synchronisation - the rank's records are copied into the fixed-size send slot,
+    all-gathered over NCCL and, on `dst_rank`, copied to a pinned host buffer.  `finish()` waits for that one copy.
+    Because nothing blocks the host in between, the caller can enqueue the next batch before it collects this one:
+    the gather of batch k overlaps the kernels of batch k + 1."""
+
+    def __init__(self, engine, device, counts, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.eng, self.group = torch, dist, engine, group
+        self.device = torch.device(device)
+        self.counts = [int(c) for c in counts]
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if len(self.counts) != self.world:
+            raise ValueError("DeviceGather: one count per rank")
+        self.cap = max(max(self.counts), 1)
+        self.words = RESULT_DTYPE.itemsize // 8
+        self.stream = torch.cuda.ExternalStream(engine.stream_handle(), device=self.device)
+        # two buffer sets, used alternately: gather k + 1 may be in flight while the host still reads gather k
+        self.slots = [{"send": torch.zeros((self.cap, self.words), dtype=torch.float64, device=self.device),
+                       "recv": torch.empty((self.world * self.cap, self.words), dtype=torch.float64, device=self.device),
+                       "host": torch.empty((self.world * self.cap, self.words), dtype=torch.float64).pin_memory(),
+                       "event": torch.cuda.Event()} for _ in range(2)]
+        self.started = 0
+
+    def start(self, ticket):
+        """Returns a handle for finish().  At most two gathers may be outstanding."""
+        torch = self.torch
+        ptr, n = self.eng.icp_batch_device_records(ticket)
+        if n != self.counts[self.rank]:
+            raise ValueError("DeviceGather: this rank's batch has %d pairs, counts say %d" % (n, self.counts[self.rank]))
+        slot = self.slots[self.started % 2]
+        self.started += 1
+        with torch.cuda.stream(self.stream):
+            if n:
+                src = torch.as_tensor(_DeviceBytes(ptr, n * self.words), device=self.device).view(n, self.words)
+                slot["send"][:n].copy_(src, non_blocking=True)
+            self.dist.all_gather_into_tensor(slot["recv"], slot["send"], group=self.group)
+            slot["host"].copy_(slot["recv"], non_blocking=True)
+            slot["event"].record(self.stream)
+        return slot
+
+    def finish(self, slot):
+        """Concatenation of all ranks' records in rank order (numpy RESULT_DTYPE)."""
+        slot["event"].synchronize()
+        host = slot["host"].numpy().reshape(self.world, self.cap, self.words)
+        return np.concatenate([host[r, :self.counts[r]].reshape(-1).view(RESULT_DTYPE).copy() for r in range(self.world)])

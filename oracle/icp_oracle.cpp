@@ -701,6 +701,55 @@ static bool plane_hypothesis(const double* pts, int n, double max_z, unsigned lo
     pl[3] = -(pl[0] * p0[0] + pl[1] * p0[1] + pl[2] * p0[2]);
     return true;
 }
+// Open3D PointCloud::SegmentPlane, last step: the final inliers of the best hypothesis (|plane . (x, y, z, 1)| < thr) and
+// GetPlaneFromPoints on them (centroid, centred second moments, the largest 2x2-determinant cross product, normalised).
+// The summation order is the convention shared with the CUDA path (plane.cu k_plane_refit): 1024 strided partial sums,
+// xor-butterfly over the 32 lanes of every warp, then over the 32 warp sums.
+static double butterfly1024(std::vector<double> v) {
+    for (int w = 0; w < 32; ++w)
+        for (int o = 16; o > 0; o >>= 1) {
+            double t[32];
+            for (int l = 0; l < 32; ++l) t[l] = v[32 * w + l] + v[32 * w + (l ^ o)];
+            for (int l = 0; l < 32; ++l) v[32 * w + l] = t[l];
+        }
+    double u[32];
+    for (int w = 0; w < 32; ++w) u[w] = v[32 * w];
+    for (int o = 16; o > 0; o >>= 1) {
+        double t[32];
+        for (int l = 0; l < 32; ++l) t[l] = u[l] + u[l ^ o];
+        for (int l = 0; l < 32; ++l) u[l] = t[l];
+    }
+    return u[0];
+}
+static void plane_refit(const double* pts, int n, double max_z, double thr, double* pl) {
+    std::vector<double> sx(1024, 0.0), sy(1024, 0.0), sz(1024, 0.0), sc(1024, 0.0);
+    auto inlier = [&](int i) {
+        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+        return z < max_z && std::fabs(pl[0] * x + pl[1] * y + pl[2] * z + pl[3]) < thr;
+    };
+    for (int i = 0; i < n; ++i)
+        if (inlier(i)) { const int t = i & 1023; sx[t] += pts[3 * (size_t)i]; sy[t] += pts[3 * (size_t)i + 1]; sz[t] += pts[3 * (size_t)i + 2]; sc[t] += 1.0; }
+    const double cnt = butterfly1024(sc);
+    const double cx = butterfly1024(sx) / cnt, cy = butterfly1024(sy) / cnt, cz = butterfly1024(sz) / cnt;
+    std::vector<double> xx(1024, 0.0), xy(1024, 0.0), xz(1024, 0.0), yy(1024, 0.0), yz(1024, 0.0), zz(1024, 0.0);
+    for (int i = 0; i < n; ++i)
+        if (inlier(i)) {
+            const int t = i & 1023;
+            const double r0 = pts[3 * (size_t)i] - cx, r1 = pts[3 * (size_t)i + 1] - cy, r2 = pts[3 * (size_t)i + 2] - cz;
+            xx[t] += r0 * r0; xy[t] += r0 * r1; xz[t] += r0 * r2; yy[t] += r1 * r1; yz[t] += r1 * r2; zz[t] += r2 * r2;
+        }
+    const double XX = butterfly1024(xx), XY = butterfly1024(xy), XZ = butterfly1024(xz), YY = butterfly1024(yy), YZ = butterfly1024(yz), ZZ = butterfly1024(zz);
+    const double det_x = YY * ZZ - YZ * YZ, det_y = XX * ZZ - XZ * XZ, det_z = XX * YY - XY * XY;
+    double a, b, c;
+    if (det_x > det_y && det_x > det_z) { a = det_x; b = XZ * YZ - XY * ZZ; c = XY * YZ - XZ * YY; }
+    else if (det_y > det_z) { a = XZ * YZ - XY * ZZ; b = det_y; c = XY * XZ - YZ * XX; }
+    else { a = XY * YZ - XZ * YY; b = XY * XZ - YZ * XX; c = det_z; }
+    const double norm = std::sqrt(a * a + b * b + c * c);
+    if (norm == 0.0) { pl[0] = pl[1] = pl[2] = pl[3] = 0.0; return; }
+    a /= norm; b /= norm; c /= norm;
+    pl[0] = a; pl[1] = b; pl[2] = c;
+    pl[3] = -(a * cx + b * cy + c * cz);
+}
 int orc_fit_plane(const double* pts, int n, double max_z, double thr, int iterations, unsigned long long seed, double* plane4) {
     int best_cnt = 0, best_h = -1;
     std::vector<int> score(iterations, 0);
@@ -718,6 +767,7 @@ int orc_fit_plane(const double* pts, int n, double max_z, double thr, int iterat
     for (int h = 0; h < iterations; ++h) if (score[h] > best_cnt) { best_cnt = score[h]; best_h = h; }
     plane4[0] = plane4[1] = plane4[2] = plane4[3] = 0;
     if (best_h >= 0) plane_hypothesis(pts, n, max_z, seed, best_h, plane4);
+    if (best_cnt >= 3) plane_refit(pts, n, max_z, thr, plane4);
     return best_cnt;
 }
 

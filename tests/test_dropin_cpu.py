@@ -171,9 +171,15 @@ def test_oracle_plane_fit_is_reproducible_and_sane():
     np.testing.assert_array_equal(pl, pl2)
     assert n_in == n2 > 0.5 * (p[:, 2] < -0.5).sum()
     assert abs(np.linalg.norm(pl[:3]) - 1) < 1e-12 and abs(abs(pl[2]) - 1) < 1e-3 and abs(abs(pl[3]) - synth.SENSOR_HEIGHT) < 0.02
-    # inlier count of the returned model, recomputed with numpy
+    # n_in counts the inliers of the winning 3-point hypothesis; the returned model is Open3D's least-squares refit to
+    # them (GetPlaneFromPoints), so it explains at least about as many points and is close to the SVD plane of its inliers
     low = p[p[:, 2] < -0.5]
-    assert (np.abs(low @ pl[:3] + pl[3]) < 0.01).sum() == n_in
+    m = np.abs(low @ pl[:3] + pl[3]) < 0.01
+    assert m.sum() >= 0.95 * n_in
+    q = low[m]
+    nn = np.linalg.svd(q - q.mean(0))[2][2]
+    nn = nn * np.sign(nn @ pl[:3])
+    assert np.abs(nn - pl[:3]).max() < 2e-3 and abs(-nn @ q.mean(0) - pl[3]) < 2e-3
     pl3, _ = orc.fit_plane(p, seed=1)
     assert np.abs(pl3 - pl).max() < 0.02                 # another seed: another, equally good, hypothesis
     # too few points below the height: no model
@@ -220,11 +226,19 @@ def test_dropin_icp2planes_on_oracle_engine(tmp_path):
         np.testing.assert_array_equal(Ts[0].array, T01.array)
         kf = kfm.KeyFrame(d, times[0], None)
         kf.load_pointcloud()
-        kf.plane_model = np.array([0.0, 0.0, 1.0, 0.69])
+        kf.fixed_plane_model = np.array([0.0, 0.0, 1.0, 0.69])
         kf.pre_process(method="icp2planes")
         assert ("fit_plane", kf._scan_id) not in fake.calls
+        np.testing.assert_array_equal(kf.plane_model, [0.0, 0.0, 1.0, 0.69])
         pw = orc.preprocess_two_planes(seq.scans[0], plane_model=[0.0, 0.0, 1.0, 0.69])
         np.testing.assert_array_equal(kf.pointcloud_ground_plane.points, pw[1][0])
+        # without a pinned model the plane is recomputed on every pre_process, as the reference does (keyframe.py:173):
+        # new points must not be split by the plane of the old ones
+        kf.fixed_plane_model = None
+        kf.set_points(seq.scans[1])
+        kf.pre_process(method="icp2planes")
+        np.testing.assert_array_equal(kf.plane_model, pre[1][0])
+        np.testing.assert_array_equal(kf.pointcloud_ground_plane.points, pre[1][1][0])
         km.unload_pointcloud(0)
         assert km.keyframes[0].pointcloud_ground_plane is None
     finally:
