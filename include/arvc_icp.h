@@ -64,6 +64,10 @@ int arvc_profile_report(arvc_ctx* ctx, char* buf, size_t cap);
  * earlier; arvc_scan_preprocess waits for it on the device. */
 int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n);
 int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n);
+/* Host wait for the upload of ONE scan (its copy-stream event): afterwards the host buffer handed to arvc_scan_upload_*
+ * may be reused.  Returns at once when the copy has already finished.  (KeyFrame.load_pointcloud recycles its pinned
+ * staging buffers with this instead of a device-wide synchronisation.) */
+int arvc_scan_wait_upload(arvc_ctx* ctx, int64_t scan_id);
 /* Forget the cached preprocessing of a scan (host-side flag only).  The reference never sets
  * KeyFrame.pre_processed (keyframe.py:39,114), i.e. every pre_process() call redoes the work; this engine caches by
  * scan id and parameters, and this call restores the reference's "redo" behaviour (used by bench.py). */
@@ -178,6 +182,7 @@ long long arvc_lzf_decompress(const unsigned char* in, size_t n_in, unsigned cha
 
 /* pinned host staging (optional; plain malloc'ed pointers work too, just slower for H2D) */
 void* arvc_host_alloc(size_t bytes);
+void* arvc_ctx_host_alloc(arvc_ctx* ctx, size_t bytes);   /* same, after selecting the context's device (for helper threads) */
 void arvc_host_free(void* p);
 
 #ifdef __cplusplus

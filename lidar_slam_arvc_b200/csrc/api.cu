@@ -373,6 +373,14 @@ int arvc_scan_invalidate(arvc_ctx* ctx, int64_t scan_id) {
 int arvc_scan_upload_f32(arvc_ctx* ctx, int64_t scan_id, const float* xyz, int n) { return upload(ctx, scan_id, xyz, n, false); }
 int arvc_scan_upload_f64(arvc_ctx* ctx, int64_t scan_id, const double* xyz, int n) { return upload(ctx, scan_id, xyz, n, true); }
 
+int arvc_scan_wait_upload(arvc_ctx* ctx, int64_t scan_id) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s) return ctx->fail(ARVC_E_STATE, "scan_wait_upload: unknown scan id");
+    if (s->up_ev) CK(cudaEventSynchronize(s->up_ev));
+    return ARVC_OK;
+}
+
 int arvc_scan_free(arvc_ctx* ctx, int64_t scan_id) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
@@ -1012,6 +1020,10 @@ void* arvc_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
     return p;
+}
+void* arvc_ctx_host_alloc(arvc_ctx* ctx, size_t bytes) {
+    if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    return arvc_host_alloc(bytes);
 }
 void arvc_host_free(void* p) { if (p) cudaFreeHost(p); }
 

@@ -47,6 +47,7 @@ constexpr int kUnionScanCap = 384;    // larger unions are split per query (lane
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
 constexpr int kFarBlocks = 296;   // blocks per pair of the far-query kernel (2 x 148 SMs)
+constexpr int kSpreadBlocks = 3552;   // three waves of search blocks (148 SMs x 8 resident): below that, queries are spread thinner
 
 __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
     const double bx0 = g.ox + cx * cl, by0 = g.oy + cy * cl, bz0 = g.oz + cz * cl;
@@ -442,12 +443,22 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
     const int n = pass == 0 ? src.counts[CNT_NPTS] : st->nlist;       // pass 0 searches every point
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
     const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
+    // Small batches leave most of the GPU idle while a warp works through its 32 queries (the groups of a warp run in
+    // lockstep, dense unions serve their queries one after the other): when the whole batch fits a few waves of blocks,
+    // every group takes only q < 8 queries - the lanes gl >= q still help with look-ups, staging and record scans - so
+    // that the pass finishes after a fraction of the latency.  q is the same for all blocks of a pair (n is).
+    int q = kG;
+    for (int c = 1; c < kG; c <<= 1) {
+        const int chunks = (n + kGroupsPerBlock * c - 1) / (kGroupsPerBlock * c);
+        if (chunks <= (int)gridDim.x && (long long)chunks * bd->n_pairs <= kSpreadBlocks) { q = c; break; }
+    }
+    const int per_chunk = kGroupsPerBlock * q;
     // late passes run on a reduced grid (a finished pair then costs few block launches): each block strides over
-    // the chunks of kIcpBlock work-list entries; the warps of a block share nothing, so no block barrier is needed
+    // the chunks of work-list entries; the warps of a block share nothing, so no block barrier is needed
 #pragma unroll 1
-    for (int chunk = blockIdx.x; chunk * kIcpBlock < n; chunk += gridDim.x) {
+    for (int chunk = blockIdx.x; chunk * per_chunk < n; chunk += gridDim.x) {
     const long long t_begin = clock64();
-    const int t_idx = chunk * kIcpBlock + threadIdx.x;
+    const int t_idx = gl < q ? chunk * per_chunk + grp * q + gl : n;
     double T[12];                        // re-read per chunk: keeping it live across the loop costs 24 registers
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->T[k];
@@ -1006,8 +1017,9 @@ template <int METHOD>
 void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, int n_pairs_grid, int pass, int combos_mask) {
     const char* nm = pass_name(pass);
     const int sh_pts = pass < 4 ? 0 : (pass < 10 ? 2 : 3), sh_search = pass < 3 ? 0 : (pass < 5 ? 1 : 2);
+    const int mult = n_pairs_grid <= 2 ? 4 : (n_pairs_grid <= 8 ? 2 : 1);      // small batches: room to spread the queries (blocks without work exit)
     const dim3 g256(max(1, ((cap_max + 255) / 256) >> sh_pts), n_pairs_grid);
-    const dim3 gsearch(max(1, gx_search >> sh_search), n_pairs_grid);
+    const dim3 gsearch(max(1, gx_search >> sh_search) * mult, n_pairs_grid);
     const dim3 gacc(max(1, ((cap_max + kAccBlockPts - 1) / kAccBlockPts) >> sh_pts), n_pairs_grid);
     void* args[] = {(void*)&d_bd};
     if (pass > 0) {
@@ -1021,7 +1033,7 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
     // far queries: a few per cent of the points; 296 blocks x 8 groups per pair stride over the pair's far list
-    const dim3 gfar(kFarBlocks, n_pairs_grid);
+    const dim3 gfar(kFarBlocks * mult, n_pairs_grid);
     if (combos_mask & 1) E.kernel("icp_far", (const void*)k_icp_far<false, false>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel("icp_far", (const void*)k_icp_far<false, true>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel("icp_far", (const void*)k_icp_far<true, false>, gfar, dim3(kIcpBlock), args);

@@ -18,7 +18,6 @@ from config import ICP_PARAMETERS
 from lidar_slam_arvc_b200 import runtime
 from lidar_slam_arvc_b200.engine import P2P, P2PLANE, Engine
 from lidar_slam_arvc_b200.homogeneousmatrix import result_type
-from lidar_slam_arvc_b200.pcd import read_pcd_xyz
 
 
 class PointCloud:
@@ -72,6 +71,8 @@ class KeyFrame():
         self.pre_processed = False               # never set by the reference either (keyframe.py:39,114)
         self.last_result = None                  # extension: fitness / inlier_rmse / iterations of the last registration
         self._scan_id = runtime.new_scan_id()
+        self._pinned_handle = None
+        self._loaded_from = None
         self._filtered_cache = None
         self._on_device = False
         self._preprocessed_on_device = False
@@ -83,21 +84,45 @@ class KeyFrame():
         self.plane_seed = 0                      # extension: seed of the reproducible RANSAC (Open3D's is unseeded)
 
     # ------------------------------------------------------------------ load / unload
-    def load_pointcloud(self):
-        filename = self.directory + '/robot0/lidar/data/' + str(self.scan_time) + '.pcd'
-        print('Reading pointcloud: ', filename)
-        self.set_points(read_pcd_xyz(filename))
+    def pcd_filename(self):
+        return self.directory + '/robot0/lidar/data/' + str(self.scan_time) + '.pcd'
 
-    def set_points(self, xyz):
+    def load_pointcloud(self):
+        """keyframe.py:41-45.  The file is parsed into a page-locked buffer (by the read-ahead thread when the previous
+        load announced it) and the upload is only enqueued: the call returns while the copy runs on the copy stream.
+        A keyframe that is still resident is not read again - the reference re-reads the same file on every call
+        (loopclosing.py:163,177), which yields the same points - so loop closing finds its keyframes preprocessed."""
+        filename = self.pcd_filename()
+        print('Reading pointcloud: ', filename)
+        if self._on_device and self._loaded_from == filename:
+            return
+        xyz, handle = runtime.get_loader().fetch(filename)
+        self.set_points(xyz, _pinned_handle=handle)
+        self._loaded_from = filename
+
+    def set_points(self, xyz, _pinned_handle=None):
         """Extension: hand the PCD payload over directly ([n,3] float32 or float64)."""
+        self._release_staging()
         self.pointcloud = PointCloud(xyz)
         runtime.get_engine().upload(self._scan_id, xyz)
+        self._pinned_handle = _pinned_handle
+        self._loaded_from = None
         self._on_device = True
         self._preprocessed_on_device = False
         self._filtered_cache = None
 
+    def _release_staging(self):
+        """Give the page-locked staging buffer back to the pool - after its copy has finished, and only then."""
+        if getattr(self, "_pinned_handle", None) is not None:
+            if self._on_device:
+                runtime.get_engine().wait_upload(self._scan_id)
+            runtime.get_loader().release(self._pinned_handle)
+        self._pinned_handle = None
+
     def unload_pointcloud(self):
         print('Removing pointclouds from memory (filtered, planes, fpfh): ')
+        self._release_staging()
+        self._loaded_from = None
         if self._on_device:
             runtime.get_engine().free(self._scan_id)
         self._on_device = False

@@ -5,6 +5,9 @@ load/unload_pointcloud, pre_process, compute_transformation); the GUI methods (d
 of the hot path.  Extension for batched callers (loop closing): `pre_process_many` and
 `compute_transformations`, which issue ONE device batch for many independent pairs.
 """
+import collections
+import os
+
 import numpy as np
 
 from config import ICP_PARAMETERS
@@ -23,6 +26,8 @@ class KeyFrameManager():
         self.voxel_size = voxel_size
         self.method = method
         self.show_registration_result = False
+        self._resident = collections.OrderedDict()      # keyframe positions with a device copy, least recently loaded first
+        self.max_resident_keyframes = int(os.environ.get("ARVC_MAX_RESIDENT_KEYFRAMES", "4096"))   # ~12 MB of HBM each at 64 beams
 
     def add_keyframes(self, keyframe_sampling):
         for i in range(0, len(self.scan_times), keyframe_sampling):
@@ -32,6 +37,7 @@ class KeyFrameManager():
     def add_keyframe(self, index):
         print('Adding keyframe with scan_time: ', self.scan_times[index])
         kf = KeyFrame(directory=self.directory, scan_time=self.scan_times[index], voxel_size=self.voxel_size)
+        kf._scan_index = index
         self.keyframes.append(kf)
 
     def load_pointclouds(self):
@@ -41,9 +47,33 @@ class KeyFrameManager():
 
     def load_pointcloud(self, i):
         self.keyframes[i].load_pointcloud()
+        self._read_ahead(i)
+        # Loop closing never unloads (loopclosing.py:163-178), and resident keyframes are what makes its second visit of a
+        # keyframe free - but device memory is finite: beyond `max_resident_keyframes` the least recently loaded ones are
+        # dropped (they come back, bit-identical, with their next load_pointcloud).
+        self._resident.pop(i, None)
+        self._resident[i] = True
+        while len(self._resident) > self.max_resident_keyframes:
+            old = next(iter(self._resident))
+            self._resident.pop(old)
+            self.keyframes[old].unload_pointcloud()
+
+    def _read_ahead(self, i):
+        """Announce the file a sequential caller will ask for next (run_scanmatcher.py:196-213 adds and loads keyframe
+        i + 1 right after registering i): the loader's helper thread reads it while the GPU registers the current pair."""
+        if i != len(self.keyframes) - 1:
+            return                                   # not the newest keyframe: random access (loop closing), no guess
+        idx = getattr(self.keyframes[i], "_scan_index", None)
+        if idx is None:
+            return
+        prev = getattr(self.keyframes[i - 1], "_scan_index", None) if i > 0 else None
+        step = idx - prev if prev is not None and idx > prev else 1
+        if idx + step < len(self.scan_times):
+            runtime.get_loader().prefetch(self.directory + '/robot0/lidar/data/' + str(self.scan_times[idx + step]) + '.pcd')
 
     def unload_pointcloud(self, i):
         self.keyframes[i].unload_pointcloud()
+        self._resident.pop(i, None)
 
     def pre_process(self, index):
         self.keyframes[index].pre_process(method=self.method)

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
     "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane", "arvc_ctx_set_option", "arvc_scan_get_counters",
-    "arvc_icp_batch_device_records",
+    "arvc_icp_batch_device_records", "arvc_scan_wait_upload", "arvc_ctx_host_alloc",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library():
     lib.arvc_scan_upload_f32.argtypes = [vp, c.c_int64, vp, c.c_int]
     lib.arvc_scan_upload_f64.argtypes = [vp, c.c_int64, vp, c.c_int]
     lib.arvc_scan_free.argtypes = [vp, c.c_int64]
+    lib.arvc_scan_wait_upload.argtypes = [vp, c.c_int64]
     lib.arvc_scan_preprocess.argtypes = [vp, c.c_int, i64p, c.POINTER(PreprocessParams)]
     lib.arvc_scan_info.argtypes = [vp, c.c_int64, ip, ip, ip, ip]
     lib.arvc_scan_get_points.argtypes = [vp, c.c_int64, dp, dp]
@@ -96,6 +97,8 @@ def load_library():
     lib.arvc_lzf_decompress.restype = c.c_longlong
     lib.arvc_host_alloc.argtypes = [c.c_size_t]
     lib.arvc_host_alloc.restype = vp
+    lib.arvc_ctx_host_alloc.argtypes = [vp, c.c_size_t]
+    lib.arvc_ctx_host_alloc.restype = vp
     lib.arvc_host_free.argtypes = [vp]
     lib.arvc_host_free.restype = None
     _lib = lib
@@ -128,6 +131,55 @@ def lzf_decompress(data, out_size):
     return out.raw[:out_size]
 
 
+class PinnedPool:
+    """Pooled page-locked host buffers (arvc_host_alloc) handed out as numpy arrays: the load path parses a PCD file
+    straight into one, so that the upload is a true asynchronous copy (keyframe.py:41-45 replacement).
+    Thread-safe: the read-ahead thread of the drop-in allocates, the main thread releases."""
+
+    def __init__(self, engine):
+        import threading
+        self.lib = load_library()
+        self.ctx = engine.h
+        self.free = []                 # (capacity, pointer)
+        self.live = {}                 # pointer -> capacity
+        self.lock = threading.Lock()
+
+    def empty(self, n_rows, dtype=np.float32):
+        """An uninitialised [n_rows, 3] array in pinned memory."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n_rows) * 3 * dtype.itemsize, 1)
+        with self.lock:
+            best = None
+            for k, (cap, ptr) in enumerate(self.free):
+                if cap >= nbytes and (best is None or cap < self.free[best][0]):
+                    best = k
+            if best is not None:
+                cap, ptr = self.free.pop(best)
+            else:
+                cap = 1 << 16
+                while cap < nbytes:
+                    cap <<= 1
+                ptr = self.lib.arvc_ctx_host_alloc(self.ctx, cap)
+                if not ptr:
+                    raise EngineError("arvc_host_alloc(%d) failed" % cap)
+            self.live[ptr] = cap
+        buf = (ctypes.c_char * cap).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n_rows) * 3).reshape(int(n_rows), 3)
+        return arr, ptr
+
+    def release(self, ptr):
+        with self.lock:
+            cap = self.live.pop(ptr, None)
+            if cap is not None:
+                self.free.append((cap, ptr))
+
+    def close(self):
+        with self.lock:
+            for cap, ptr in self.free:
+                self.lib.arvc_host_free(ptr)
+            self.free = []
+
+
 class Engine:
     """One context = one GPU + one stream.  Not thread-safe (calls are serialised by the caller, like the reference)."""
 
@@ -140,10 +192,20 @@ class Engine:
         self.h = h
         self.device = int(device)
         self._n_raw = {}                  # raw size of every uploaded scan (output capacity of map_build)
+        self._pinned = None
+
+    @property
+    def pinned(self):
+        """The context's pool of page-locked staging buffers (created on first use)."""
+        if self._pinned is None:
+            self._pinned = PinnedPool(self)
+        return self._pinned
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.arvc_ctx_destroy(self.h)
+            self.lib.arvc_ctx_destroy(self.h)      # synchronises: no copy from a staging buffer is in flight afterwards
+            if self._pinned is not None:
+                self._pinned.close()
             self.h = None
 
     def __del__(self):
@@ -173,6 +235,10 @@ class Engine:
     def upload_ptr(self, scan_id, ptr, n):
         self._ck(self.lib.arvc_scan_upload_f32(self.h, int(scan_id), ctypes.c_void_p(ptr), int(n)))
         self._n_raw[int(scan_id)] = int(n)
+
+    def wait_upload(self, scan_id):
+        """Host wait for the copy of one scan (its pinned staging buffer may be reused afterwards)."""
+        self._ck(self.lib.arvc_scan_wait_upload(self.h, int(scan_id)))
 
     def free(self, scan_id):
         self._ck(self.lib.arvc_scan_free(self.h, int(scan_id)))

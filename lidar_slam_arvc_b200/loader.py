@@ -1,0 +1,60 @@
+"""Load path of the drop-in KeyFrame (reference: keyframemanager/keyframe.py:41-45, where
+`o3d.io.read_point_cloud` reads one PCD file synchronously per `load_pointcloud()` call).
+
+`ScanLoader` reads PCD files into page-locked buffers of the engine's pool, so that the host -> device copy that
+follows is a true asynchronous copy on the engine's copy stream, and it reads AHEAD: while the caller registers the
+pair (i, i + 1) - a synchronous call - one helper thread already reads and parses the file of scan i + 2.  The
+reference's loop (run_scanmatcher.py:196-213) calls load_pointcloud(i + 2) next, which then only enqueues the copy.
+With an engine that has no pinned pool (the CPU test double) the loader degrades to plain numpy arrays.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+from .pcd import read_pcd_xyz
+
+
+class ScanLoader:
+    def __init__(self, engine):
+        self.engine = engine
+        self.pool = getattr(engine, "pinned", None)
+        self.executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="arvc-readahead")
+        self.pending = {}                # filename -> Future of (array, pinned handle)
+        self.stats = {"read_ahead_hits": 0, "reads": 0}
+
+    def _read(self, filename):
+        handle = [None]
+
+        def alloc(n_rows, dtype):
+            arr, handle[0] = self.pool.empty(n_rows, dtype)
+            return arr
+
+        xyz = read_pcd_xyz(filename, alloc=alloc if self.pool is not None else None)
+        return xyz, handle[0]
+
+    def prefetch(self, filename):
+        """Start reading `filename` in the background (no-op when it is already pending or does not exist)."""
+        if filename in self.pending or not os.path.exists(filename):
+            return
+        if len(self.pending) >= 4:       # a caller that never comes back for its read-ahead must not pile up buffers
+            old = next(iter(self.pending))
+            self.release(self.pending.pop(old).result()[1])
+        self.pending[filename] = self.executor.submit(self._read, filename)
+
+    def fetch(self, filename):
+        """(xyz, pinned handle or None): the read-ahead result when there is one, else a synchronous read."""
+        self.stats["reads"] += 1
+        fut = self.pending.pop(filename, None)
+        if fut is not None:
+            self.stats["read_ahead_hits"] += 1
+            return fut.result()
+        return self._read(filename)
+
+    def release(self, handle):
+        if handle is not None and self.pool is not None:
+            self.pool.release(handle)
+
+    def close(self):
+        for fut in self.pending.values():
+            self.release(fut.result()[1])
+        self.pending = {}
+        self.executor.shutdown(wait=True)

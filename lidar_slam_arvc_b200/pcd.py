@@ -11,8 +11,10 @@ _NP = {("F", 4): "<f4", ("F", 8): "<f8", ("I", 1): "<i1", ("I", 2): "<i2", ("I",
        ("U", 1): "<u1", ("U", 2): "<u2", ("U", 4): "<u4", ("U", 8): "<u8"}
 
 
-def read_pcd_xyz(filename):
-    """Returns an [n,3] array: float32 when the file stores float32 coordinates (the usual case), else float64."""
+def read_pcd_xyz(filename, alloc=None):
+    """Returns an [n,3] array: float32 when the file stores float32 coordinates (the usual case), else float64.
+    `alloc(n_rows, dtype)` may supply the output array (e.g. page-locked memory for an asynchronous upload); a binary file
+    that holds nothing but float32 x y z is then read straight into it."""
     with open(filename, "rb") as f:
         header = {}
         while True:
@@ -49,6 +51,12 @@ def read_pcd_xyz(filename):
                 for c in range(cnt):
                     names.append("%s_%d" % (base, c))
                     formats.append(dt)
+        if data == "binary" and alloc is not None and names == ["x", "y", "z"] and formats == ["<f4"] * 3:
+            out = alloc(n, np.float32)
+            got = f.readinto(memoryview(out).cast("B")) if n else 0
+            if got != 12 * n:
+                raise ValueError("%s: truncated PCD payload" % filename)
+            return out
         if data == "binary":
             rec = np.dtype({"names": names, "formats": formats})
             arr = np.frombuffer(f.read(rec.itemsize * n), dtype=rec, count=n)
@@ -74,6 +82,11 @@ def read_pcd_xyz(filename):
         else:
             raise ValueError("%s: unknown DATA %s" % (filename, data))
     out_t = np.float32 if all(c.dtype == np.float32 for c in cols) else np.float64
+    if alloc is not None:
+        out = alloc(len(cols[0]), out_t)
+        for k in range(3):
+            out[:, k] = cols[k]
+        return out
     return np.ascontiguousarray(np.stack(cols, axis=1).astype(out_t, copy=False))
 
 

@@ -20,8 +20,23 @@ def get_engine():
 
 
 def set_engine(engine):
-    global _engine
+    global _engine, _loader
+    if _loader is not None:
+        _loader.close()
+        _loader = None
     _engine = engine
+
+
+_loader = None
+
+
+def get_loader():
+    """The process-wide PCD loader (pinned staging + read-ahead) bound to the current engine."""
+    global _loader
+    if _loader is None:
+        from .loader import ScanLoader
+        _loader = ScanLoader(get_engine())
+    return _loader
 
 
 def new_scan_id():

@@ -139,6 +139,95 @@ def test_loop_closing_triangle_one_device_batch(kfm_module, tmp_path):
         assert np.abs(T2 - want).max() < 1e-4
 
 
+def test_loop_closing_keyframe_cache_survives_between_invocations(kfm_module, tmp_path):
+    """SURVEY.md §8 f-1, second half: a keyframe that loop closing has loaded and preprocessed stays resident, so the next
+    loop_closing_triangle invocation neither reads its PCD again nor launches any preprocessing kernel for it (the
+    reference re-reads and re-estimates normals on every visit, loopclosing.py:163-178: same results, repeated work)."""
+    from test_loopclosing_cpu import FakeGraphSLAM, noisy_estimate, small_loop_sequence
+    for m in [k for k in sys.modules if k.split(".")[0] == "graphslam"]:
+        del sys.modules[m]
+    import graphslam.loopclosing as lc_mod
+    seq = small_loop_sequence()
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq)
+    km = kfm_module.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icppointplane")
+    km.add_keyframes(keyframe_sampling=1)
+    est = noisy_estimate(seq)
+    g1 = FakeGraphSLAM(est, HomogeneousMatrix(np.eye(4)))
+    g2 = FakeGraphSLAM(est, HomogeneousMatrix(np.eye(4)))
+    last = len(seq.poses) - 1
+    eng, loader = runtime.get_engine(), runtime.get_loader()
+    np.random.seed(3)
+    lc_mod.LoopClosing(g1).loop_closing_triangle(current_index=last, number_of_triplets_loop_closing=4, keyframe_manager=km)
+    reads = loader.stats["reads"]
+    assert reads > 0
+    # second invocation, same candidates: only registration kernels run
+    eng.sync()
+    eng.profile_enable(True)
+    np.random.seed(3)
+    lc_mod.LoopClosing(g2).loop_closing_triangle(current_index=last, number_of_triplets_loop_closing=4, keyframe_manager=km)
+    prof = eng.profile_report()
+    eng.profile_enable(False)
+    assert loader.stats["reads"] == reads                                       # no PCD was read again
+    assert prof and all(k.startswith("icp_") for k in prof), sorted(prof)       # no filter / sort / grid / normals kernel
+    assert len(g1.edges) == len(g2.edges) > 0
+    for (i, j, T, _), (i2, j2, T2, _) in zip(g1.edges, g2.edges):
+        assert (i, j) == (i2, j2)
+        np.testing.assert_array_equal(T, T2)
+    # an unloaded keyframe comes back with its next load (bit-identical results)
+    touched = sorted({k for e in g1.edges for k in e[:2]})
+    km.unload_pointcloud(touched[0])
+    g3 = FakeGraphSLAM(est, HomogeneousMatrix(np.eye(4)))
+    np.random.seed(3)
+    lc_mod.LoopClosing(g3).loop_closing_triangle(current_index=last, number_of_triplets_loop_closing=4, keyframe_manager=km)
+    assert loader.stats["reads"] == reads + 1
+    for (_, _, T, _), (_, _, T3, _) in zip(g1.edges, g3.edges):
+        np.testing.assert_array_equal(T, T3)
+
+
+def test_load_path_pinned_read_ahead_overlaps_registration(kfm_module, tmp_path):
+    """load_pointcloud parses the PCD into a page-locked buffer (read ahead by a helper thread for a
+    sequential caller) and only ENQUEUES the upload on the copy stream - it does not wait for the registration batch that
+    occupies the compute stream.  Proof: the uploads of four keyframes complete while that batch is still running."""
+    import time
+    seq = synth.Sequence(6, synth.OS1_64, start=30.0)
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq)
+    km = kfm_module.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icppointplane")
+    eng, loader = runtime.get_engine(), runtime.get_loader()
+    for i in (0, 1):
+        km.add_keyframe(i)
+        km.load_pointcloud(i)
+        km.pre_process(i)
+    assert km.keyframes[1]._pinned_handle is not None                # staged in page-locked memory
+    eng.sync()
+    hits0 = loader.stats["read_ahead_hits"]
+    ip = eng.make_icp_params()
+    n_rep = 120                                                       # a batch that keeps the compute stream busy for tens of ms
+    init = np.repeat(seq.relative_odo(0, 1)[None], n_rep, axis=0)
+    t0 = time.perf_counter()
+    ticket = eng.icp_batch_async([km.keyframes[0]._scan_id] * n_rep, [km.keyframes[1]._scan_id] * n_rep, init, ip)
+    for i in range(2, 6):
+        km.add_keyframe(i)
+        km.load_pointcloud(i)                                         # returns after enqueueing the copy
+    for i in range(2, 6):
+        eng.wait_upload(km.keyframes[i]._scan_id)
+    t_up = time.perf_counter() - t0
+    rec = eng.icp_batch_finish(ticket)
+    t_icp = time.perf_counter() - t0
+    assert t_up < 0.5 * t_icp, (t_up, t_icp)                          # the copies did not queue behind the batch
+    assert loader.stats["read_ahead_hits"] >= hits0 + 2               # scans 3.. were already parsed when asked for
+    assert (rec["updates"] == rec["updates"][0]).all()
+    # and the overlapped uploads are the right data
+    km.pre_process(2)
+    T12 = km.compute_transformation(1, 2, HomogeneousMatrix(seq.relative_odo(1, 2)))
+    pre = [orc.preprocess(seq.scans[k]) for k in (1, 2)]
+    ref = orc.icp(pre[1][0], pre[0][0], pre[0][1], seq.relative_odo(1, 2), orc.P2PLANE)
+    assert np.abs(T12.array - ref.transformation).max() < 1e-4
+    for i in range(6):
+        km.unload_pointcloud(i)
+
+
 def test_icp2planes_method(kfm_module, tmp_path):
     """'icp2planes' through the drop-in (keyframe.py:164-189, 262-295): preprocess -> plane -> split -> two point-to-plane
     registrations in one batch -> component merge, against the same pipeline on the oracle."""
