@@ -181,7 +181,7 @@ class LoopClosureWorkload:
         jobs = [(self.world_model, self.synth.OS1_64, self.poses[k], 10000 + k) for k in todo]
         if self.workers > 1 and len(jobs) > 2:
             import multiprocessing as mp
-            with mp.get_context("fork").Pool(min(self.workers, len(jobs))) as pool:
+            with mp.get_context("fork").Pool(min(self.workers, len(jobs)), initializer=self.synth._pool_init) as pool:
                 out = pool.map(self.synth._scan_job, jobs, chunksize=max(1, len(jobs) // (4 * self.workers)))
         else:
             out = [self.synth._scan_job(j) for j in jobs]

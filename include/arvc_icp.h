@@ -47,7 +47,9 @@ void* arvc_stream(arvc_ctx* ctx);                 /* the context's cudaStream_t 
 int arvc_version(void);
 /* Engine switches (0 / 1), for A/B measurements and parity tests; results never depend on them:
  *   "icp_loop_graph"  1 (default): registration loops are ONE CUDA graph whose WHILE node ends the iteration on the
- *                     device with the last convergence; 0: max_iter + 1 passes are enqueued unconditionally. */
+ *                     device with the last convergence; 0: max_iter + 1 passes are enqueued unconditionally.
+ *   "normals_tap"     0 (default); 1: scans preprocessed from now on also record the neighbour set of every normal
+ *                     (arvc_scan_get_neighbors) - separate kernel instantiations, max_nn x 4 bytes per point. */
 int arvc_ctx_set_option(arvc_ctx* ctx, const char* name, int value);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t arvc_kernel_launches(const arvc_ctx* ctx);
@@ -127,6 +129,12 @@ int arvc_scan_split_plane(arvc_ctx* ctx, int64_t src_id, const double* plane /* 
 int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_index);
 int arvc_scan_get_voxels(arvc_ctx* ctx, int64_t scan_id, int32_t* keys, int32_t* counts);
 int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count);
+/* Neighbour SETS behind the normals (KDTreeSearchParamHybrid: the max_nn nearest, then d2 < radius^2; keyframe.py:160-162):
+ * for every queried point (cloud order) the cloud indices of the neighbours whose covariance gave its normal, in no
+ * particular order, padded with -1 to max_nn per row; out_cnt[q] = their number.  Only for scans preprocessed while the
+ * context option "normals_tap" was set (the production kernels do not record anything). */
+int arvc_scan_get_neighbors(arvc_ctx* ctx, int64_t scan_id, int n_query, const int32_t* point_ids, int32_t* out_idx /* [n_query*max_nn] */,
+                            int32_t* out_cnt /* [n_query] */);
 /* Device counters of a preprocessed scan, counters[16]: 0 points after the filter, 1 final points, 2 error flags,
  * 3 occupied grid cells (all levels), 4 normals recomputed in canonical order, 5 points served by the per-point
  * normals kernel, 6 blocks / 7 single points the block kernel handed back, 8 blocks served at a trial radius. */

@@ -85,6 +85,7 @@ struct arvc_ctx {
         return e;
     }
     IcpGraphCache icp_graphs;
+    bool normals_tap = false;           // arvc_ctx_set_option("normals_tap", 1): record the neighbour sets of the normals
     bool icp_use_graph = true;          // ARVC_ICP_LOOP=unrolled / arvc_ctx_set_option("icp_loop_graph", 0) switch it off
 
     void* pinned_get(size_t bytes, size_t* got) {
@@ -208,9 +209,12 @@ int upload(arvc_ctx* ctx, int64_t id, const void* xyz, int n, bool f64) {
 }
 
 // device buffers that outlive preprocessing
-void plan_persistent(SlabPlanner& P, Scan& s, bool wide, bool voxel_on, unsigned table_cap) {
+void plan_persistent(SlabPlanner& P, Scan& s, bool wide, bool voxel_on, unsigned table_cap, int tap_nn) {
     const size_t cap = (size_t)std::max(s.n_raw, 1);
     ScanDev& d = s.dev;
+    d.tap_cnt = tap_nn > 0 ? P.take<int>(cap) : nullptr;
+    d.tap_idx = tap_nn > 0 ? P.take<int>(cap * (size_t)tap_nn) : nullptr;
+    d.tap_stride = tap_nn;
     d.counts = P.take<int>(CNT_WORDS);
     d.recs = wide ? (void*)P.take<RecD>(cap) : (void*)P.take<RecF>(cap);
     d.normals = P.take<double>(cap * 4);
@@ -289,6 +293,7 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
 int arvc_ctx_set_option(arvc_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return ARVC_E_ARG;
     if (std::string(name) == "icp_loop_graph") { ctx->icp_use_graph = value != 0; return ARVC_OK; }
+    if (std::string(name) == "normals_tap") { ctx->normals_tap = value != 0; return ARVC_OK; }
     return ctx->fail(ARVC_E_ARG, std::string("ctx_set_option: unknown option ") + name);
 }
 
@@ -460,14 +465,16 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         const unsigned tfac = getenv("ARVC_TABLE_FACTOR") ? (unsigned)atoi(getenv("ARVC_TABLE_FACTOR")) : (c0 < 0.12 ? 8u : 4u);
         while (tcap < tfac * (unsigned)std::max(s->n_raw, 1)) tcap <<= 1;      // finer grids occupy more cells
         if (s->slab) { cudaFreeAsync(s->slab, ctx->L.stream); s->slab = nullptr; }
+        const int tap_nn = (ctx->normals_tap && want_normals) ? p->max_nn : 0;
         SlabPlanner pp;
-        plan_persistent(pp, *s, wide, voxel_on, tcap);
+        plan_persistent(pp, *s, wide, voxel_on, tcap, tap_nn);
         s->slab_bytes = pp.off;
         CK(cudaMallocAsync(&s->slab, s->slab_bytes, ctx->L.stream));
         SlabPlanner pq;
         pq.base = reinterpret_cast<char*>(s->slab);
         s->dev = ScanDev{};
-        plan_persistent(pq, *s, wide, voxel_on, tcap);
+        plan_persistent(pq, *s, wide, voxel_on, tcap, tap_nn);
+        if (tap_nn > 0) CK(cudaMemsetAsync(s->dev.tap_cnt, 0, sizeof(int) * (size_t)std::max(s->n_raw, 1), ctx->L.stream));
         s->dev.raw = s->d_raw; s->dev.n_raw = s->n_raw; s->dev.raw_f64 = s->f64 ? 1 : 0; s->dev.cap = std::max(s->n_raw, 1);
         s->dev.wide = wide ? 1 : 0; s->dev.table_mask = tcap - 1; s->dev.grid = g;
         ScanDev tmp = s->dev;
@@ -493,7 +500,7 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     for (Scan* s : todo) tmax = std::max(tmax, s->dev.table_mask + 1u);
     ctx->L.launch("clear_scan", k_clear_scan, dim3(std::min(256u, (tmax + 255u) / 256u), (unsigned)todo.size()), dim3(256), (const ScanDev*)d_batch);
     run_preprocess(ctx->L, d_batch, (int)todo.size(), cap_max, fp, vp, voxel_on);
-    if (want_normals) run_normals(ctx->L, d_batch, (int)todo.size(), cap_max, np, any_wide, any_narrow);
+    if (want_normals) run_normals(ctx->L, d_batch, (int)todo.size(), cap_max, np, any_wide, any_narrow, ctx->normals_tap);
 
     // ---- publish the persistent device descriptors used by the ICP kernels
     for (Scan* s : todo) {
@@ -753,6 +760,42 @@ int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count) {
         const int idx = s->dev.wide ? reinterpret_cast<const RecD*>(hr.data())[p].idx : reinterpret_cast<const RecF*>(hr.data())[p].idx;
         nn_count[idx] = hc[p];
     }
+    return ARVC_OK;
+}
+
+int arvc_scan_get_neighbors(arvc_ctx* ctx, int64_t scan_id, int n_query, const int32_t* point_ids, int32_t* out_idx, int32_t* out_cnt) {
+    if (!ctx) return ARVC_E_ARG;
+    Scan* s = ctx->find(scan_id);
+    if (!s || !s->preprocessed || !s->has_normals) return ctx->fail(ARVC_E_STATE, "scan_get_neighbors: no normals");
+    if (!s->dev.tap_idx) return ctx->fail(ARVC_E_STATE, "scan_get_neighbors: preprocess the scan with the context option \"normals_tap\" set");
+    if (n_query < 0 || (n_query > 0 && (!point_ids || !out_idx || !out_cnt))) return ctx->fail(ARVC_E_ARG, "scan_get_neighbors: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int c[CNT_WORDS];
+    const int rc = fetch_counts(ctx, s, c);
+    if (rc) return rc;
+    const int n = c[CNT_NPTS], K = s->dev.tap_stride;
+    // cloud order -> Morton position
+    std::vector<char> hr((size_t)n * (s->dev.wide ? sizeof(RecD) : sizeof(RecF)));
+    std::vector<int> hcnt(std::max(n, 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(hr.data(), s->dev.recs, hr.size(), cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaMemcpyAsync(hcnt.data(), s->dev.tap_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->L.stream));
+        CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    std::vector<int> pos(std::max(n, 1), -1);
+    for (int p = 0; p < n; ++p) {
+        const int idx = s->dev.wide ? reinterpret_cast<const RecD*>(hr.data())[p].idx : reinterpret_cast<const RecF*>(hr.data())[p].idx;
+        if (idx >= 0 && idx < n) pos[idx] = p;
+    }
+    for (int q = 0; q < n_query; ++q) {
+        const int id = point_ids[q];
+        if (id < 0 || id >= n || pos[id] < 0) return ctx->fail(ARVC_E_ARG, "scan_get_neighbors: point id out of range");
+        const int p = pos[id], cnt = std::min(hcnt[p], K);
+        out_cnt[q] = hcnt[p];
+        for (int k = 0; k < K; ++k) out_idx[(size_t)q * K + k] = -1;
+        if (cnt > 0) CK(cudaMemcpyAsync(out_idx + (size_t)q * K, s->dev.tap_idx + (size_t)p * K, sizeof(int) * cnt, cudaMemcpyDeviceToHost, ctx->L.stream));
+    }
+    CK(cudaStreamSynchronize(ctx->L.stream));
     return ARVC_OK;
 }
 

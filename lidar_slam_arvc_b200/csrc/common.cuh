@@ -135,6 +135,9 @@ struct ScanDev {
     int* raw_index;         // [cap] raw index of filtered point k (filter order)
     int* vox_keys;          // [cap][3] voxel index of output point k (voxel mode)
     int* vox_counts;        // [cap]
+    int* tap_idx;           // parity tap (ctx option "normals_tap"): [cap][max_nn] cloud indices of the neighbours each normal used
+    int* tap_cnt;           //                                         [cap] how many of them (Morton order), else null
+    int tap_stride;         // = max_nn of the preprocessing the tap was recorded with
     GridSpec grid;
     // scratch (valid during preprocessing only)
     double* fx; double* fy; double* fz;      // filtered cloud, filter order

@@ -140,8 +140,8 @@ struct IcpGraphCache {
 
 void run_preprocess(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const FilterParams& fp, const VoxelParams& vp,
                     bool voxel_on);
-void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow);
-void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np);
+void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool any_wide, bool any_narrow, bool tap);
+void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool tap);
 // Enqueues the whole iteration of a batch.  `use_graph`: device-terminated loop (CUDA graph with a WHILE node); else
 // max_iter + 1 passes are enqueued unconditionally (finished pairs turn into no-ops).  Returns the graph used (or null).
 const IcpGraph* run_icp(Launcher& L, IcpGraphCache& cache, const BatchDesc& h_bd, BatchDesc* d_bd_batch, int src_cap_max, int combos_mask,

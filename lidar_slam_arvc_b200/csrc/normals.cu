@@ -174,7 +174,9 @@ template <> struct CandEval<true> {
 //         eigen-solve to k_normals_eigen (one THREAD per point - the solve is scalar work);
 // mode 1: only the points k_normals_eigen flagged as ill-conditioned: same search, then the canonical re-summation
 //         and the solve inside the warp.
-template <bool WIDE>
+// TAP: record which neighbours were used (parity tap of arvc_scan_get_neighbors); a separate instantiation, so that the
+// production kernels carry none of it.
+template <bool WIDE, bool TAP>
 __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalParams& np, const int mode, const int p, unsigned char* s_raw) {
     typedef typename RecT<WIDE>::type Rec;
     const int w = threadIdx.x >> 5, lane = lane_id();
@@ -277,7 +279,16 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
     const uint2* runs = runs_full;
     int nruns = nfull;
     if (np.debug & 2) { nfull = 0; ntry = 0; total = 0; }      // ablation: fixed per-point overhead only
-    auto accumulate = [&](double x, double y, double z) {
+    const bool tap = TAP && mode != 1 && s.tap_idx != nullptr;      // the canonical re-summation (mode 1) uses the same set
+    auto tap_reset = [&]() {
+        if (tap) { __syncwarp(); if (lane == 0) s.tap_cnt[p] = 0; __syncwarp(); }
+    };
+    tap_reset();
+    auto accumulate = [&](double x, double y, double z, int idx) {
+        if (tap) {
+            const int slot = atomicAdd(&s.tap_cnt[p], 1);
+            if (slot < s.tap_stride) s.tap_idx[(size_t)p * s.tap_stride + slot] = idx;
+        }
         const double ux = x - qx, uy = y - qy, uz = z - qz;      // centred: exact differences of float32 payloads
         sx += ux; sy += uy; sz += uz;
         sxx = fma(ux, ux, sxx); sxy = fma(ux, uy, sxy); sxz = fma(ux, uz, sxz);
@@ -332,13 +343,13 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
                 auto take_one = [&](const CandEval<WIDE>& c, unsigned j) {
                     const float u = c.d2f * bsf;
                     if (u < u_lo) {
-                        accumulate(c.x(), c.y(), c.z());
+                        accumulate(c.x(), c.y(), c.z(), c.idx());
                     } else if (u <= u_hi) {
                         const double d2 = c.exact(qx, qy, qz);
                         if (d2 < rq2) {
                             const int b = min(kBins - 1, (int)(d2 * bin_scale));
                             if (b < blo) {
-                                accumulate(c.x(), c.y(), c.z());
+                                accumulate(c.x(), c.y(), c.z(), c.idx());
                             } else if (b <= bhi) {
                                 const int slot = atomicAdd(ncand_s, 1);
                                 if (slot < kCand) { cand_d2[slot] = d2; cand_idx[slot] = c.idx(); cand_pos[slot] = (int)j; }
@@ -372,7 +383,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
                             bool have = false;
                             if (in_radius(c, d2, have)) {
                                 const int b = bstar == kBins ? 0 : bucket(c, d2, have);
-                                if (b < bstar) accumulate(c.x(), c.y(), c.z());
+                                if (b < bstar) accumulate(c.x(), c.y(), c.z(), c.idx());
                                 else if (b == bstar) { hit = true; if (!have) d2 = c.exact(qx, qy, qz); }
                             }
                         }
@@ -397,7 +408,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
         if (!trial && tot > np.max_nn && 3 * tot <= kSpecFactor3 * np.max_nn) {
             pass_b(kBins);
             if (warp_sum(cnt) <= np.max_nn) settled = true;
-            else { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0; cnt = 0; }
+            else { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0; cnt = 0; tap_reset(); }
         }
         if (settled) break;
         if (tot > np.max_nn) {
@@ -481,7 +492,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
                         double x, y, z;
                         int idx;
                         load_rec(recs + cand_pos[a], x, y, z, idx);
-                        accumulate(x, y, z);
+                        accumulate(x, y, z, idx);
                     }
                     if (rank == need - 1) { td2 = d2a; tidx = ia; have_tau = true; }
                 }
@@ -520,6 +531,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
                 // ... and redo the accumulation with the exact threshold
                 sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0;
                 cnt = 0;
+                tap_reset();
                 for (int rr = 0; rr < nruns; ++rr) {
                     const uint2 run = runs[rr];
                     for (unsigned u = run.x + lane; u < run.y; u += 32) {
@@ -527,7 +539,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
                         int idx;
                         load_rec(recs + u, x, y, z, idx);
                         const double d2 = sqdist(qx, qy, qz, x, y, z);
-                        if (d2 < rq2 && !key_less(tau_d2, tau_idx, d2, idx)) accumulate(x, y, z);
+                        if (d2 < rq2 && !key_less(tau_d2, tau_idx, d2, idx)) accumulate(x, y, z, idx);
                     }
                 }
             }
@@ -639,7 +651,7 @@ __device__ __forceinline__ void normals_point(const ScanDev& s, const NormalPara
     }
 }
 
-template <bool WIDE>
+template <bool WIDE, bool TAP>
 __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __restrict__ scans, NormalParams np, int mode) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const ScanDev& s = scans[blockIdx.y];
@@ -648,13 +660,13 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
     const int w = threadIdx.x >> 5;
     if (mode == 0) {
         const int p = blockIdx.x * kNrmWarps + w;
-        if (p < n) normals_point<WIDE>(s, np, 0, p, s_raw);
+        if (p < n) normals_point<WIDE, TAP>(s, np, 0, p, s_raw);
     } else if (mode == 2) {
         // the points the block kernel (normals_blk.cu) could not serve from its shared tile: same search, per point
         const int nfb = s.counts[CNT_NFB];
         for (int q = blockIdx.x * kNrmWarps + w; q < nfb; q += gridDim.x * kNrmWarps) {
             const int p = s.fb_list[q];
-            if (p < n) normals_point<WIDE>(s, np, 0, p, s_raw);
+            if (p < n) normals_point<WIDE, TAP>(s, np, 0, p, s_raw);
             __syncwarp();
         }
     } else {
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(kNrmWarps * 32, 3) k_normals(const ScanDev* __
         const int nredo = s.counts[CNT_NREDO];
         for (int q = blockIdx.x * kNrmWarps + w; q < nredo; q += gridDim.x * kNrmWarps) {
             const int p = s.redo_list[q];
-            if (p < n) normals_point<WIDE>(s, np, 1, p, s_raw);
+            if (p < n) normals_point<WIDE, TAP>(s, np, 1, p, s_raw);
             __syncwarp();
         }
     }
@@ -694,7 +706,7 @@ __global__ void __launch_bounds__(128) k_normals_eigen(const ScanDev* __restrict
     reinterpret_cast<double4*>(s.normals)[p] = make_double4(nv.x, nv.y, nv.z, 0.0);
 }
 
-void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np_in, bool any_wide, bool any_narrow) {
+void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np_in, bool any_wide, bool any_narrow, bool tap) {
     if (n_scans == 0 || cap_max == 0) return;
     NormalParams np = np_in;
     np.r2 = np.radius * np.radius;
@@ -710,24 +722,27 @@ void run_normals(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, 
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((attr_set >> (dev & 63)) & 1ull)) {
-        cudaFuncSetAttribute(k_normals<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_normals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_normals<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_normals<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_normals<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_normals<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set |= 1ull << (dev & 63);
     }
+    auto point_kernel = [&](bool wide) { return wide ? (tap ? k_normals<true, true> : k_normals<true, false>) : (tap ? k_normals<false, true> : k_normals<false, false>); };
     // float32 records (the PCD payload, voxel off): block-cooperative kernel + per-point kernel for what it hands back;
     // float64 records (voxel means, float64 uploads): per-point kernel.  ARVC_NORMALS_IMPL=point forces the latter.
     static const bool per_point_only = getenv("ARVC_NORMALS_IMPL") && std::string(getenv("ARVC_NORMALS_IMPL")) == "point";
-    if (any_narrow && per_point_only) L.launch_smem("normals", k_normals<false>, grid, block, smem_sel, d_scans, np, 0);
+    if (any_narrow && per_point_only) L.launch_smem("normals", point_kernel(false), grid, block, smem_sel, d_scans, np, 0);
     if (any_narrow && !per_point_only) {
-        launch_normals_blk(L, d_scans, n_scans, cap_max, np);
-        L.launch_smem("normals_fallback", k_normals<false>, dim3(min(grid.x, 192u), n_scans), block, smem_sel, d_scans, np, 2);
+        launch_normals_blk(L, d_scans, n_scans, cap_max, np, tap);
+        L.launch_smem("normals_fallback", point_kernel(false), dim3(min(grid.x, 192u), n_scans), block, smem_sel, d_scans, np, 2);
     }
-    if (any_wide) L.launch_smem("normals", k_normals<true>, grid, block, smem_sel, d_scans, np, 0);
+    if (any_wide) L.launch_smem("normals", point_kernel(true), grid, block, smem_sel, d_scans, np, 0);
     L.launch("normals_eigen", k_normals_eigen, dim3((cap_max + 127) / 128, n_scans), dim3(128), d_scans);
     // ill-conditioned points (a few per cent)
     const dim3 grid_redo(min(grid.x, 96u), n_scans);
-    if (any_narrow) L.launch_smem("normals_redo", k_normals<false>, grid_redo, block, smem, d_scans, np, 1);
-    if (any_wide) L.launch_smem("normals_redo", k_normals<true>, grid_redo, block, smem, d_scans, np, 1);
+    if (any_narrow) L.launch_smem("normals_redo", point_kernel(false), grid_redo, block, smem, d_scans, np, 1);
+    if (any_wide) L.launch_smem("normals_redo", point_kernel(true), grid_redo, block, smem, d_scans, np, 1);
 }
 
 }  // namespace arvc

@@ -109,6 +109,7 @@ __device__ __forceinline__ int compact_runs(NbShared& S, bool valid, unsigned st
 #ifndef ARVC_NBOCC
 #define ARVC_NBOCC 4
 #endif
+template <bool TAP>      // TAP: record the neighbour indices every normal used (parity tap, separate instantiation)
 __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const ScanDev* __restrict__ scans, NormalParams np) {
     extern __shared__ __align__(16) unsigned char nb_smem[];
     NbShared& S = *reinterpret_cast<NbShared*>(nb_smem);
@@ -284,7 +285,17 @@ __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const Sc
         const double qx = (double)qxf, qy = (double)qyf, qz = (double)qzf;
         double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
         int cnt = 0;
+        const int p = p0 + ql;
+        const bool tap = TAP && s.tap_idx != nullptr;
+        auto tap_reset = [&]() {
+            if (tap) { __syncwarp(); if (lane == 0) s.tap_cnt[p] = 0; __syncwarp(); }
+        };
+        tap_reset();
         auto accumulate = [&](const float4& v) {
+            if (tap) {
+                const int slot = atomicAdd(&s.tap_cnt[p], 1);
+                if (slot < s.tap_stride) s.tap_idx[(size_t)p * s.tap_stride + slot] = __float_as_int(v.w);
+            }
             const double ux = (double)v.x - qx, uy = (double)v.y - qy, uz = (double)v.z - qz;      // exact differences
             sx += ux; sy += uy; sz += uz;
             sxx = fma(ux, ux, sxx); sxy = fma(ux, uy, sxy); sxz = fma(ux, uz, sxz);
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const Sc
             // count; only when more than K turn up is the work discarded and the selection run
             take_all();
             if (ntile <= K || warp_sum(cnt) <= K) settled = true;
-            else { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0; cnt = 0; }
+            else { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0; cnt = 0; tap_reset(); }
         }
         if (!settled) {
             // ---- sweep A: d2 histogram of the in-radius candidates.  float32 bucket coordinate (error < 1e-3 buckets):
@@ -413,8 +424,8 @@ __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const Sc
                 }
             }
         }
-        const int p = p0 + ql;
         if (failed) {
+            tap_reset();
             if (lane == 0) {
                 s.fb_list[atomicAdd(&s.counts[CNT_NFB], 1)] = p;
                 atomicAdd(&s.counts[CNT_NFB_POINTS], 1);
@@ -452,16 +463,18 @@ __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const Sc
     }
 }
 
-void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np) {
+void launch_normals_blk(Launcher& L, const ScanDev* d_scans, int n_scans, int cap_max, const NormalParams& np, bool tap) {
     static unsigned long long attr_set = 0;      // per device: the attribute belongs to the device's copy of the kernel
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((attr_set >> (dev & 63)) & 1ull)) {
-        cudaFuncSetAttribute(k_normals_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbShared));
+        cudaFuncSetAttribute(k_normals_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbShared));
+        cudaFuncSetAttribute(k_normals_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbShared));
         attr_set |= 1ull << (dev & 63);
     }
     const dim3 grid((cap_max + kNbG - 1) / kNbG, n_scans);
-    L.launch_smem("normals", k_normals_blk, grid, dim3(kNbThreads), sizeof(NbShared), d_scans, np);
+    if (tap) L.launch_smem("normals", k_normals_blk<true>, grid, dim3(kNbThreads), sizeof(NbShared), d_scans, np);
+    else L.launch_smem("normals", k_normals_blk<false>, grid, dim3(kNbThreads), sizeof(NbShared), d_scans, np);
 }
 
 }  // namespace arvc

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
     "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane", "arvc_ctx_set_option", "arvc_scan_get_counters",
-    "arvc_icp_batch_device_records", "arvc_scan_wait_upload", "arvc_ctx_host_alloc",
+    "arvc_icp_batch_device_records", "arvc_scan_wait_upload", "arvc_ctx_host_alloc", "arvc_scan_get_neighbors",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library():
     lib.arvc_scan_get_voxels.argtypes = [vp, c.c_int64, ip, ip]
     lib.arvc_scan_get_nn_counts.argtypes = [vp, c.c_int64, ip]
     lib.arvc_scan_get_counters.argtypes = [vp, c.c_int64, ip]
+    lib.arvc_scan_get_neighbors.argtypes = [vp, c.c_int64, c.c_int, ip, ip, ip]
     lib.arvc_ctx_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.arvc_icp_batch.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), dp, dp, dp, ip, ip]
     lib.arvc_icp_batch_async.argtypes = [vp, c.c_int, i64p, i64p, dp, c.POINTER(IcpParams), c.POINTER(c.c_uint64)]
@@ -316,6 +317,15 @@ class Engine:
         cnt = np.empty(max(n, 1), dtype=np.int32)
         self._ck(self.lib.arvc_scan_get_nn_counts(self.h, int(scan_id), _ip(cnt)))
         return cnt[:n]
+
+    def get_neighbors(self, scan_id, point_ids, max_nn):
+        """Neighbour index sets of the normals of `point_ids` (cloud order): list of sorted int arrays.  Needs
+        set_option("normals_tap", 1) before the scan is preprocessed."""
+        ids = np.ascontiguousarray(point_ids, dtype=np.int32).reshape(-1)
+        out = np.full((max(len(ids), 1), int(max_nn)), -1, dtype=np.int32)
+        cnt = np.zeros(max(len(ids), 1), dtype=np.int32)
+        self._ck(self.lib.arvc_scan_get_neighbors(self.h, int(scan_id), len(ids), _ip(ids), _ip(out), _ip(cnt)))
+        return [np.sort(out[k, :cnt[k]]) for k in range(len(ids))]
 
     COUNTER_NAMES = ("n_filtered", "n_points", "error_flags", "grid_cells", "normals_redone", "normals_per_point",
                      "normals_blocks_handed_back", "normals_points_handed_back", "normals_trial_blocks", "dbg_tile_records",

@@ -66,7 +66,7 @@ class _DeviceBytes:
     without a copy (plumbing only: torch.distributed needs a tensor to hand to NCCL)."""
 
     def __init__(self, ptr, n_words):
-        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<f8", "data": (int(ptr), True), "version": 3}
+        self.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
 
 
 class DeviceGather:
