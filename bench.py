@@ -54,7 +54,9 @@ def parse_args():
     ap.add_argument("--lc-pairs", type=int, default=10000, help="N>1: loop-closure pairs of the global list (BASELINE config 4)")
     ap.add_argument("--lc-scans", type=int, default=464, help="keyframes of the loop-closure trajectory (two laps of the synthetic corridor)")
     ap.add_argument("--lc-batch", type=int, default=2048, help="N>1: pairs per device batch (the gather of batch k overlaps batch k+1)")
-    ap.add_argument("--lc-pairs-n1", type=int, default=1500, help="N=1 extra: leading pairs of the same sorted global list timed on one GPU")
+    ap.add_argument("--lc-pairs-n1", type=int, default=0, help="N=1 extra: leading pairs of the sorted global list timed on one GPU (0 = the whole list)")
+    ap.add_argument("--lc-balance", default="history", choices=["history", "count"],
+                    help="N>1: contiguous shard bounds by the previous batch's per-pair passes (equal work) or by pair count")
     ap.add_argument("--parity-pairs", type=int, default=4, help="N>1: pairs per rank checked against the oracle after the timed regions")
     return ap.parse_args()
 
@@ -652,25 +654,30 @@ def config3_line(args, torch, engine, synth, eng, stream):
 
 
 def config4_single(args, torch, engine, eng, stream):
-    n4 = min(args.lc_pairs_n1, args.lc_pairs)
+    """The WHOLE global list of the N > 1 runs on one GPU, same device batches: the strong-scaling reference."""
     wl = LoopClosureWorkload(args.lc_scans, args.lc_pairs, max(1, os.cpu_count() or 1))
-    tg4, sr4, init4 = wl.tg[:n4] + 5000, wl.sr[:n4] + 5000, wl.init[:n4]
+    n4 = len(wl.tg) if args.lc_pairs_n1 <= 0 else min(args.lc_pairs_n1, len(wl.tg))
+    off = 1 << 20                                     # scan ids apart from everything else in this context
+    tg4, sr4, init4 = wl.tg[:n4] + off, wl.sr[:n4] + off, wl.init[:n4]
     scans4 = np.unique(np.concatenate([wl.tg[:n4], wl.sr[:n4]]))
     wl.materialise(scans4)
     pin4 = pin_scans(torch, [wl.scans[int(k)] for k in scans4])
-    ids4 = scans4 + 5000
+    ids4 = scans4 + off
     pp = eng.make_preprocess_params()
     ip = eng.make_icp_params(engine.P2PLANE)
+    B = max(1, args.lc_batch)
     for k, t in zip(ids4, pin4):
         eng.upload_ptr(int(k), t.data_ptr(), t.shape[0])
 
     def step4():
         eng.invalidate(ids4)
         eng.preprocess(ids4, pp)
-        return eng.icp_batch(tg4, sr4, init4, ip)
-    steps4 = max(2, args.steps // 4)
+        tickets = [eng.icp_batch_async(tg4[s0:s0 + B], sr4[s0:s0 + B], init4[s0:s0 + B], ip) for s0 in range(0, n4, B)]
+        return np.concatenate([eng.icp_batch_finish(t) for t in tickets])
+    steps4 = 2
     ms, own4 = timed_steps(torch, stream, eng, step4, steps4, warm=1)
-    out = {"workload": "configs[3] on one GPU: the first %d pairs of the sorted global list of %d loop-closure pairs (%d scans touched)" % (n4, args.lc_pairs, len(ids4)),
+    out = {"workload": "configs[3] on one GPU: %d of the %d loop-closure pairs of the sorted global list (%d scans touched), device batches of <= %d pairs"
+                       % (n4, len(wl.tg), len(ids4), B),
            "value": n4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_pair": ms / n4, "steps": steps4,
            "mean_icp_updates": float(np.mean(own4["updates"])), "max_icp_updates": int(own4["updates"].max()),
            "note": "the strong-scaling reference for the N > 1 lines (same list, same code path, scans resident, device time)"}
@@ -684,58 +691,94 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     wl = LoopClosureWorkload(args.lc_scans, args.lc_pairs, max(1, (os.cpu_count() or 1) // world))
     G = len(wl.tg)
-    lo, hi = sharding.shard_bounds(G, world, rank)
-    tg, sr, init = wl.tg[lo:hi], wl.sr[lo:hi], wl.init[lo:hi]
-    my_scans = sharding.scans_of_pairs(tg, sr)
-    wl.materialise(my_scans)
-    pinned = pin_scans(torch, [wl.scans[int(k)] for k in my_scans])
-    h2d_bytes = int(sum(t.numel() * 4 for t in pinned) + init.nbytes + tg.nbytes + sr.nbytes)
+    if G < world:
+        raise SystemExit("no loop-closure candidates: --lc-scans %d must cover more than one lap (232 keyframes) of the synthetic corridor" % args.lc_scans)
+    # Shard bounds can move between steps (see `rebalance`), so a rank keeps host copies of every scan the list touches;
+    # it UPLOADS and preprocesses only the scans of its current shard.
+    all_scans = sharding.scans_of_pairs(wl.tg, wl.sr)
+    wl.materialise(all_scans)
+    pinned = dict(zip([int(k) for k in all_scans], pin_scans(torch, [wl.scans[int(k)] for k in all_scans])))
 
     eng = engine.Engine(local_rank)
     pp = eng.make_preprocess_params()
     ip = eng.make_icp_params(engine.P2PLANE)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     B = max(1, args.lc_batch)
-    shard_sizes = [sharding.shard_bounds(G, world, r)[1] - sharding.shard_bounds(G, world, r)[0] for r in range(world)]
-    n_batches = max((n + B - 1) // B for n in shard_sizes)
-    gathers = [sharding.DeviceGather(eng, dev, [min(B, max(0, n - b * B)) for n in shard_sizes]) for b in range(n_batches)]
-    busy_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    gather = sharding.DeviceGather(eng, dev, B)
+    state = {"bounds": [sharding.shard_bounds(G, world, r)[0] for r in range(world)] + [G], "resident": set()}
 
-    def upload_all():
-        for k, t in zip(my_scans, pinned):
-            eng.upload_ptr(int(k), t.data_ptr(), t.shape[0])
+    busy_buf = torch.zeros(world, dtype=torch.float64, device=dev)
 
-    bounds = growing_chunks(len(my_scans))
+    def rebalance(records, bounds, busy_ms):
+        """Run-time load balancer.  Cost history of the batch that has just been gathered: every rank holds all records
+        (passes per pair) and learns every rank's measured busy time (one 8-byte all-gather); a pair's cost estimate is
+        (3 + passes) x the time its rank needed per such unit, and the contiguous shard bounds of the NEXT batch equalise
+        the summed estimates.  The first batch is split by pair count.  A loop-closing back end sees the same places again
+        and again (run_graphSLAM.py:259-263), which is what makes a cost history meaningful; here the list repeats exactly."""
+        if args.lc_balance != "history":
+            return
+        mine = torch.tensor([busy_ms], dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(busy_buf, mine)
+        busy = busy_buf.cpu().numpy()
+        cost = 3.0 + records["passes"].astype(np.float64)
+        for r in range(world):
+            seg = cost[bounds[r]:bounds[r + 1]]
+            if len(seg) and seg.sum() > 0 and busy[r] > 0:
+                cost[bounds[r]:bounds[r + 1]] = seg * (busy[r] / seg.sum())
+        state["bounds"] = sharding.balanced_bounds(cost, world)
 
     def step(upload, ev=None):
-        """One pass over this rank's shard.  Batch b + 1 is enqueued before batch b is collected, so the all-gather and the
-        device -> host copy of batch b overlap the kernels of batch b + 1; nothing but the final collect blocks the host."""
-        if ev:
-            ev[0].record(stream)
+        """One pass over this rank's shard of the global list.  Batch b + 1 is enqueued before batch b is collected, so the
+        all-gather and the device -> host copy of batch b overlap the kernels of batch b + 1."""
+        bounds = state["bounds"]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+        tg, sr, init = wl.tg[lo:hi], wl.sr[lo:hi], wl.init[lo:hi]
+        my_scans = sharding.scans_of_pairs(tg, sr)
+        ev = ev or (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(stream)
+        for k in state["resident"] - set(int(x) for x in my_scans):      # scans that left the shard with the last rebalancing
+            eng.free(k)
         if upload:
-            for a, b in zip(bounds[:-1], bounds[1:]):
-                for k in range(a, b):
-                    eng.upload_ptr(int(my_scans[k]), pinned[k].data_ptr(), pinned[k].shape[0])
+            ch = growing_chunks(len(my_scans))
+            for a, b in zip(ch[:-1], ch[1:]):
+                for k in my_scans[a:b]:
+                    eng.upload_ptr(int(k), pinned[int(k)].data_ptr(), pinned[int(k)].shape[0])
                 eng.preprocess(my_scans[a:b], pp)
         else:
+            for k in my_scans:
+                if int(k) not in state["resident"]:
+                    eng.upload_ptr(int(k), pinned[int(k)].data_ptr(), pinned[int(k)].shape[0])
             eng.invalidate(my_scans)
             eng.preprocess(my_scans, pp)
+        state["resident"] = set(int(x) for x in my_scans)
+        n_batches = max((n + B - 1) // B for n in sizes)
         pending, parts = [], []
         for b in range(n_batches):
             s0, s1 = min(b * B, len(tg)), min((b + 1) * B, len(tg))
             ticket = eng.icp_batch_async(tg[s0:s1], sr[s0:s1], init[s0:s1].reshape(-1, 4, 4), ip)
-            if ev and b == n_batches - 1:
+            if b == n_batches - 1:
                 ev[1].record(stream)                      # end of this rank's own work of the step (before its last gather)
-            pending.append((ticket, gathers[b], gathers[b].start(ticket)))
+            pending.append((ticket, gather.start(ticket, [min(B, max(0, n - b * B)) for n in sizes])))
             if len(pending) > 1:
-                t, g, slot = pending.pop(0)
-                parts.append(g.finish(slot))
+                t, slot = pending.pop(0)
+                parts.append(gather.finish(slot))
                 eng.icp_batch_finish(t)
         while pending:
-            t, g, slot = pending.pop(0)
-            parts.append(g.finish(slot))
+            t, slot = pending.pop(0)
+            parts.append(gather.finish(slot))
             eng.icp_batch_finish(t)
-        return parts
+        # the gathered batches, back in the order of the global list
+        out = np.zeros(G, dtype=engine.RESULT_DTYPE)
+        for b, part in enumerate(parts):
+            off = 0
+            for r in range(world):
+                n = min(B, max(0, sizes[r] - b * B))
+                out[bounds[r] + b * B: bounds[r] + b * B + n] = part[off:off + n]
+                off += n
+        info = {"pairs": hi - lo, "scans": len(my_scans), "bounds": list(bounds), "h2d": int(sum(pinned[int(k)].numel() * 4 for k in my_scans))}
+        rebalance(out, bounds, ev[0].elapsed_time(ev[1]))
+        return out, info
 
     def barrier():
         eng.sync()
@@ -746,22 +789,22 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     clocks.start()
     for _ in range(max(args.warmup, 3)):
-        upload_all()
         step(False)
         step(True)
     eng.sync()
 
     # ---- value: scans resident in HBM
-    upload_all()
+    step(False)
     barrier()
     l0 = eng.kernel_launches()
     tw0 = time.perf_counter()
+    busy_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     step_ms = []
     for s in range(args.steps):
         ts0 = time.perf_counter()
-        parts = step(False, busy_ev[s])
+        records, info = step(False, busy_ev[s])
         step_ms.append(round((time.perf_counter() - ts0) * 1e3, 1))
     ev1.record(stream)
     barrier()
@@ -773,14 +816,14 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
     dev_ms = float(t_ms.item())
     value = G * args.steps / (dev_ms * 1e-3)
 
-    # ---- e2e: host scans -> all records on rank 0's host, every step
+    # ---- e2e: host scans -> all records on every rank's host, every step
     step(True)
     barrier()
     t0 = time.perf_counter()
     e2e_step_ms = []
     for _ in range(args.steps):
         ts0 = time.perf_counter()
-        parts = step(True)
+        records, info = step(True)
         e2e_step_ms.append(round((time.perf_counter() - ts0) * 1e3, 1))
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -791,52 +834,44 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
     dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
     e2e_value = G * args.steps / float(t_s.item())
 
-    # ---- the gathered list is the global list: every rank's records, in rank order, batch by batch
-    gathered = {}
-    for b, part in enumerate(parts):
-        off = 0
-        for r in range(world):
-            n = min(B, max(0, shard_sizes[r] - b * B))
-            base = sharding.shard_bounds(G, world, r)[0] + b * B
-            for k in range(n):
-                gathered[base + k] = part[off + k]
-            off += n
-    assert len(gathered) == G, (len(gathered), G)
-    own = np.array([gathered[lo + k] for k in range(hi - lo)])
-
     # ---- parity: a sample of THIS rank's loop-closure pairs against the oracle (same run, after the timed regions)
-    from oracle import oracle as orc
+    lo, hi = info["bounds"][rank], info["bounds"][rank + 1]
     npar = min(args.parity_pairs, hi - lo)
-    sample = [int(v) for v in np.linspace(0, hi - lo - 1, npar).round()] if npar else []
-    _, cpu_dt, refs, _ = oracle_loop_closure(wl, [lo + k for k in sample], max(1, (os.cpu_count() or 1) // world))
-    rep = parity_report([own[k] for k in sample], refs, "rank %d: pairs %s of its shard" % (rank, sample))
-    info = {"rank": rank, "pairs": int(hi - lo), "scans": int(len(my_scans)), "busy_ms_per_step": busy_ms, "device_ms_per_step": dev_ms_own / args.steps,
-            "mean_icp_updates": float(np.mean(own["updates"])), "launches": int(launches), "h2d_bytes_per_step": h2d_bytes, "parity": rep}
+    sample = [lo + int(v) for v in np.linspace(0, hi - lo - 1, npar).round()] if npar else []
+    _, cpu_dt, refs, _ = oracle_loop_closure(wl, sample, max(1, (os.cpu_count() or 1) // world))
+    rep = parity_report([records[k] for k in sample], refs, "rank %d: pairs %s of the global list (its shard)" % (rank, sample))
+    mine = {"rank": rank, "pairs": int(info["pairs"]), "scans": int(info["scans"]), "busy_ms_per_step": busy_ms, "device_ms_per_step": dev_ms_own / args.steps,
+            "mean_icp_updates": float(np.mean(records["updates"][lo:hi])) if hi > lo else 0.0, "launches": int(launches), "h2d_bytes_per_step": info["h2d"],
+            "parity": rep}
     infos = [None] * world
-    dist.all_gather_object(infos, info)
+    dist.all_gather_object(infos, mine)
 
     if rank == 0:
-        gather_us = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config4(G, args.lc_scans, world, B), "ms_per_pair": dev_ms / (args.steps * G),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum(i["h2d_bytes_per_step"] for i in infos)),
-                        "d2h_bytes_per_step": int(160 * G + 164 * G), "ms_per_step": float(t_s.item()) / args.steps * 1e3},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum(i["h2d_bytes_per_step"] for i in infos) + wl.init.nbytes + 16 * G),
+                        "d2h_bytes_per_step": int(160 * G * world + 164 * G), "ms_per_step": float(t_s.item()) / args.steps * 1e3},
                 "gpu_launches": int(sum(i["launches"] for i in infos)), "clocks": clk, "step_ms": step_ms, "e2e_step_ms": e2e_step_ms,
                 "per_rank": [{k: v for k, v in i.items() if k != "parity"} for i in infos],
-                "per_gpu_rate_pairs_per_s": float(np.mean([i["pairs"] / (i["busy_ms_per_step"] * 1e-3) for i in infos])),
-                "gather": {"records_bytes_per_rank_per_batch": int(160 * min(B, max(shard_sizes))), "batches_per_step": n_batches,
+                "per_gpu_rate_pairs_per_s": float(np.mean([i["pairs"] / (i["busy_ms_per_step"] * 1e-3) for i in infos if i["pairs"]])),
+                "sharding": {"balance": args.lc_balance, "bounds": info["bounds"],
+                             "note": "contiguous shards of the (target, source)-sorted list; 'history': bounds re-placed after every batch from the passes "
+                                     "the gathered records report (equal summed cost), 'count': equal pair counts"},
+                "gather": {"records_bytes_per_rank_per_batch": int(160 * min(B, max(i["pairs"] for i in infos))), "batches_per_step": int(max((i["pairs"] + B - 1) // B for i in infos)),
                            "exposed_ms_per_step": float(max(0.0, dev_ms_own / args.steps - busy_ms)),
                            "note": "all_gather_into_tensor straight from the engine's device records on the engine's stream + one D2H on every rank; "
                                    "exposed = rank 0's step time minus its own kernels' time (gather of the last batch + waiting for the slowest rank)"},
+                "mean_icp_updates": float(np.mean(records["updates"])),
                 "parity_check": {"ok": all(i["parity"]["ok"] for i in infos), "per_rank": [i["parity"] for i in infos]},
                 "roofline": None,
                 "notes": {"strong_scaling_reference": "the N=1 line's `config4_single_gpu` runs the leading pairs of the same list on one GPU; "
                                                       "per_gpu_rate_pairs_per_s is the same quantity measured inside this run (pairs / own busy time, mean over ranks)",
                           "roofline": "per-kernel roofline is reported by the N=1 line (same kernels); a multi-rank run carries no per-launch events",
                           "reference_arm": "bench.py --impl reference --gpus N times --ref-pairs loop-closure pairs of the same list per step"}}
-        del gather_us
         print(json.dumps(line), flush=True)
+    gather.close()
+    del gather
     eng.close()
     ok = all(i["parity"]["ok"] for i in infos)
     dist.barrier()

@@ -78,17 +78,14 @@ class DeviceGather:
     Because nothing blocks the host in between, the caller can enqueue the next batch before it collects this one:
     the gather of batch k overlaps the kernels of batch k + 1."""
 
-    def __init__(self, engine, device, counts, group=None):
+    def __init__(self, engine, device, capacity, group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.eng, self.group = torch, dist, engine, group
         self.device = torch.device(device)
-        self.counts = [int(c) for c in counts]
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        if len(self.counts) != self.world:
-            raise ValueError("DeviceGather: one count per rank")
-        self.cap = max(max(self.counts), 1)
+        self.cap = max(int(capacity), 1)              # most records one rank contributes to one gather
         self.words = RESULT_DTYPE.itemsize // 8
         self.stream = torch.cuda.ExternalStream(engine.stream_handle(), device=self.device)
         # two buffer sets, used alternately: gather k + 1 may be in flight while the host still reads gather k
@@ -98,13 +95,16 @@ class DeviceGather:
                        "event": torch.cuda.Event()} for _ in range(2)]
         self.started = 0
 
-    def start(self, ticket):
-        """Returns a handle for finish().  At most two gathers may be outstanding."""
+    def start(self, ticket, counts):
+        """`counts`: records every rank contributes (known to all ranks from the sharding).  Returns a handle for finish().
+        At most two gathers may be outstanding."""
         torch = self.torch
+        counts = [int(c) for c in counts]
         ptr, n = self.eng.icp_batch_device_records(ticket)
-        if n != self.counts[self.rank]:
-            raise ValueError("DeviceGather: this rank's batch has %d pairs, counts say %d" % (n, self.counts[self.rank]))
+        if len(counts) != self.world or n != counts[self.rank] or max(counts) > self.cap:
+            raise ValueError("DeviceGather: this rank's batch has %d pairs, counts say %s (capacity %d)" % (n, counts, self.cap))
         slot = self.slots[self.started % 2]
+        slot["counts"] = counts
         self.started += 1
         with torch.cuda.stream(self.stream):
             if n:
@@ -119,4 +119,24 @@ class DeviceGather:
         """Concatenation of all ranks' records in rank order (numpy RESULT_DTYPE)."""
         slot["event"].synchronize()
         host = slot["host"].numpy().reshape(self.world, self.cap, self.words)
-        return np.concatenate([host[r, :self.counts[r]].reshape(-1).view(RESULT_DTYPE).copy() for r in range(self.world)])
+        return np.concatenate([host[r, :slot["counts"][r]].reshape(-1).view(RESULT_DTYPE).copy() for r in range(self.world)])
+
+    def close(self):
+        """Drop the device buffers while the engine's stream still exists (torch records an event on every stream a block
+        was used on when it frees the block)."""
+        self.torch.cuda.synchronize(self.device)
+        self.slots = []
+
+
+def balanced_bounds(costs, world_size):
+    """Contiguous shard bounds [world_size + 1] with (nearly) equal summed cost: scan locality of the sorted pair list is
+    kept, the shards differ in length instead of in work."""
+    c = np.cumsum(np.asarray(costs, dtype=np.float64))
+    n = len(c)
+    if n == 0:
+        return [0] * (world_size + 1)
+    inner = [int(np.searchsorted(c, c[-1] * r / world_size)) for r in range(1, world_size)]
+    b = [0] + inner + [n]
+    for k in range(1, len(b)):                       # monotone, and no shard past the end
+        b[k] = min(max(b[k], b[k - 1]), n)
+    return b
