@@ -563,6 +563,38 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
             // coarse levels pay off only where the scan is sparse; dense unions are left to the per-query search
             if (lu >= 2 && utotal > kUnionCandCap) break;
             float f1 = INFINITY, f2 = INFINITY;     // two smallest screened float32 distances (multiset)
+            // The sweeps below are branch-free: they only track the two smallest float32 distances and WHERE the smallest
+            // one was seen.  Afterwards the lane settles its query exactly: every staged record that could beat or tie
+            // with the best so far has a float32 distance <= thr (see ScreenThr), so if the second smallest one is above
+            // thr the only candidate is the record at `jmin` - one exact evaluation.  Otherwise (two records within the
+            // float32 error of each other: duplicates, near ties) the lane re-reads the union and decides every record
+            // below thr exactly, as a plain sequential scan.  Results are those of an all-float64 search.
+            auto resolve = [&](int jmin, float m1, float m2) {
+                if constexpr (!TW) {
+                    if (!(m1 <= thr) || jmin < 0) return;
+                    const float4* __restrict__ tr4 = reinterpret_cast<const float4*>(trecs);
+                    {
+                        const float4 v = __ldg(tr4 + jmin);
+                        const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                        const int idx = __float_as_int(v.w);
+                        if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = jmin; thr = screen_thr(d2); }
+                    }
+                    if (m2 <= thr) {
+                        for (int rr = 0; rr < nr; ++rr) {
+                            const uint2 run = runs[rr];
+                            for (unsigned p = run.x; p < run.y; ++p) {
+                                const float4 v = __ldg(tr4 + p);
+                                const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) {
+                                    const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                                    const int idx = __float_as_int(v.w);
+                                    if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = (int)p; thr = screen_thr(d2); }
+                                }
+                            }
+                        }
+                    }
+                }
+            };
             if (!TW && utotal > kUnionScanCap) {
                 // Dense union: every lane screening every record would cost lanes x records.  Serve the wanting lanes one
                 // at a time instead: the 8 lanes split the records of the cells that touch that lane's own ball (the
@@ -572,15 +604,12 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
                     if (!__shfl_sync(gmask, (int)want, k, kG)) continue;
                     const double qx = __shfl_sync(gmask, sx, k, kG), qy = __shfl_sync(gmask, sy, k, kG), qz = __shfl_sync(gmask, sz, k, kG);
                     const double qr = __shfl_sync(gmask, r, k, kG);
-                    Best lb;
-                    lb.d2 = __shfl_sync(gmask, b.d2, k, kG); lb.idx = __shfl_sync(gmask, b.idx, k, kG); lb.pos = -1;
                     const int kx0 = (cell_coord(qx - qr, g.ox, g.inv_c0) >> lu) - x0, kx1 = (cell_coord(qx + qr, g.ox, g.inv_c0) >> lu) - x0;
                     const int ky0 = (cell_coord(qy - qr, g.oy, g.inv_c0) >> lu) - y0, ky1 = (cell_coord(qy + qr, g.oy, g.inv_c0) >> lu) - y0;
                     const int kz0 = (cell_coord(qz - qr, g.oz, g.inv_c0) >> lu) - z0, kz1 = (cell_coord(qz + qr, g.oz, g.inv_c0) >> lu) - z0;
                     const float qxf = (float)qx, qyf = (float)qy, qzf = (float)qz;
-                    const float qe = (float)(fmax(fabs(qx), fmax(fabs(qy), fabs(qz))) * 6.0e-8 + 1e-30);
-                    const ScreenThr qscreen(qe);
-                    float qthr = qscreen(lb.d2), g1 = INFINITY, g2 = INFINITY;
+                    float g1 = INFINITY, g2 = INFINITY;
+                    int gj = -1;
                     for (int rr = 0; rr < nr; ++rr) {
                         const unsigned rc = rcell[rr];
                         const int ox = (int)(rc & 255u), oy = (int)((rc >> 8) & 255u), oz = (int)(rc >> 16);
@@ -598,36 +627,30 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
                                 const float4 v = v4[u];
                                 const float dx = qxf - v.x, dy = qyf - v.y, dz = qzf - v.z;
                                 const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));     // +inf for the padding lanes
+                                gj = d2f < g1 ? (int)(p0 + u * kG) : gj;
                                 g2 = fminf(g2, fmaxf(g1, d2f));
                                 g1 = fminf(g1, d2f);
-                                if (d2f <= qthr) {
-                                    const double d2 = sqdist(qx, qy, qz, (double)v.x, (double)v.y, (double)v.z);
-                                    const int idx = __float_as_int(v.w);
-                                    if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); qthr = qscreen(d2); }
-                                }
                             }
                         }
                     }
 #pragma unroll
                     for (int o = kG / 2; o > 0; o >>= 1) {
-                        const double od2 = __shfl_xor_sync(gmask, lb.d2, o, kG);
-                        const int oidx = __shfl_xor_sync(gmask, lb.idx, o, kG);
-                        const int opos = __shfl_xor_sync(gmask, lb.pos, o, kG);
-                        if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
                         const float h1 = __shfl_xor_sync(gmask, g1, o, kG), h2 = __shfl_xor_sync(gmask, g2, o, kG);
+                        const int hj = __shfl_xor_sync(gmask, gj, o, kG);
                         g2 = fminf(fmaxf(g1, h1), fminf(g2, h2));      // two smallest of the merged multisets
+                        gj = h1 < g1 ? hj : gj;
                         g1 = fminf(g1, h1);
                     }
-                    if (gl == k) {
-                        if (lb.pos >= 0) b = lb;
+                    if (gl == k) {      // the lane that owns the query settles it (ties between lanes show up as g2 == g1 <= thr)
                         f1 = g1; f2 = g2;
+                        resolve(gj, g1, g2);
                     }
                 }
             } else
             if constexpr (!TW) {
                 float4* stage = s_stage[grp];
                 int* spos = s_spos[grp];
-                int rr = 0;
+                int rr = 0, jmin = -1;
                 unsigned off = 0;
                 while (rr < nr) {
                     int fill = 0;
@@ -654,16 +677,13 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
                         const float4 v = stage[j];
                         const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
                         const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        jmin = d2f < f1 ? spos[j] : jmin;
                         f2 = fminf(f2, fmaxf(f1, d2f));
                         f1 = fminf(f1, d2f);
-                        if (want && d2f <= thr) {
-                            const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
-                            const int idx = __float_as_int(v.w);
-                            if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = spos[j]; thr = screen_thr(d2); }
-                        }
                     }
                     __syncwarp(gmask);
                 }
+                if (want) resolve(jmin, f1, f2);
             } else {
                 for (int rr = 0; rr < nr; ++rr) {
                     const uint2 run = runs[rr];
