@@ -46,6 +46,9 @@ constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may 
 constexpr int kUnionScanCap = 384;    // larger unions are split per query (lanes share the records of one query)
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
 constexpr int kStage = 64;        // records staged in shared memory per group and round
+#ifndef ARVC_STAGE_BULK
+#define ARVC_STAGE_BULK 0
+#endif
 constexpr int kFarBlocks = 296;   // blocks per pair of the far-query kernel (2 x 148 SMs)
 constexpr int kSpreadBlocks = 3552;   // three waves of search blocks (148 SMs x 8 resident): below that, queries are spread thinner
 
@@ -428,8 +431,18 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
-    __shared__ int s_spos[kGroupsPerBlock][kStage];
     __shared__ uint4 s_stk[kGroupsPerBlock][kStack];      // the union phase's run table
+    __shared__ int s_roff[kGroupsPerBlock][kUnionMax + 1];   // prefix sums of the runs' lengths (flat candidate index -> run)
+#if ARVC_STAGE_BULK
+    __shared__ __align__(8) unsigned long long s_mbar[kGroupsPerBlock];
+    if ((threadIdx.x & (kG - 1)) == 0) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(&s_mbar[threadIdx.x / kG]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned mbar_phase = 0;
+#endif
 
     if ((int)blockIdx.y >= bd->n_pairs) return;
     const PairDev& pr = bd->pairs[blockIdx.y];
@@ -649,38 +662,100 @@ __global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __res
             } else
             if constexpr (!TW) {
                 float4* stage = s_stage[grp];
-                int* spos = s_spos[grp];
-                int rr = 0, jmin = -1;
-                unsigned off = 0;
-                while (rr < nr) {
-                    int fill = 0;
-                    while (rr < nr && fill < kStage) {
-                        const uint2 run = runs[rr];
-                        const unsigned len = min(run.y - run.x - off, (unsigned)(kStage - fill));
-                        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(trecs + run.x + off);
-                        for (unsigned q = gl; q < len; q += 2 * kG) {      // two loads in flight per lane
-                            const bool two = q + kG < len;
-                            const float4 v0 = __ldg(src4 + q);
-                            float4 v1 = v0;
-                            if (two) v1 = __ldg(src4 + q + kG);
-                            stage[fill + q] = v0;
-                            spos[fill + q] = (int)(run.x + off + q);
-                            if (two) { stage[fill + q + kG] = v1; spos[fill + q + kG] = (int)(run.x + off + q + kG); }
-                        }
-                        fill += (int)len;
-                        off += len;
-                        if (run.x + off >= run.y) { ++rr; off = 0; }
+                int* roff = s_roff[grp];
+                int jmin = -1;
+                // The union's records form one flat sequence (the runs back to back): prefix sums of the run lengths map a
+                // flat index to its run, so that staging needs no per-run loop - short runs (a handful of records per fine
+                // cell) would leave most lanes idle.  Lane gl owns runs 8 gl .. 8 gl + 7 for the scan.
+                {
+                    int loc = 0, tmp[kUnionMax / kG];
+#pragma unroll
+                    for (int k = 0; k < kUnionMax / kG; ++k) {
+                        const int r = gl * (kUnionMax / kG) + k;
+                        tmp[k] = loc;
+                        loc += r < nr ? (int)(runs[r].y - runs[r].x) : 0;
                     }
+                    int inc = loc;
+#pragma unroll
+                    for (int o = 1; o < kG; o <<= 1) {
+                        const int t = __shfl_up_sync(gmask, inc, o, kG);
+                        if (gl >= o) inc += t;
+                    }
+#pragma unroll
+                    for (int k = 0; k < kUnionMax / kG; ++k) {
+                        const int r = gl * (kUnionMax / kG) + k;
+                        if (r < nr) roff[r] = inc - loc + tmp[k];
+                    }
+                    if (gl == 0) roff[nr] = utotal;
                     __syncwarp(gmask);
+                }
+                // flat index of a staged record -> its position in the target's record array (6 halving steps over <= 64 runs)
+                auto flat_to_pos = [&](int f) -> int {
+                    int lo = 0, hi = nr - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (roff[mid] <= f) lo = mid; else hi = mid - 1;
+                    }
+                    return (int)runs[lo].x + (f - roff[lo]);
+                };
+#if ARVC_STAGE_BULK
+                // Variant: one bulk asynchronous copy (cp.async.bulk, the non-tensor TMA path) per run piece, completion through
+                // the group's mbarrier.  Measured slower than per-record LDGSTS for these short runs - kept
+                // selectable for the comparison.
+                unsigned long long* mbar = &s_mbar[grp];
+                const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(mbar);
+                for (int base = 0; base < utotal; base += kStage) {
+                    const int fill = min(kStage, utotal - base);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the last round before async writes
+                    if (gl == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_a), "r"(fill * 16) : "memory");
+                    __syncwarp(gmask);
+                    for (int c = gl; c < nr; c += kG) {
+                        const int lo = max(roff[c], base), hi = min(roff[c + 1], base + fill);
+                        if (lo < hi) {
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (lo - base));
+                            const TRec* src_p = trecs + runs[c].x + (unsigned)(lo - roff[c]);
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"(dst), "l"(src_p), "r"((hi - lo) * 16), "r"(mbar_a) : "memory");
+                        }
+                    }
+                    {
+                        unsigned done = 0;
+                        while (!done)
+                            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                         : "=r"(done) : "r"(mbar_a), "r"(mbar_phase) : "memory");
+                        mbar_phase ^= 1u;
+                    }
+#else
+                int cur = 0;
+                for (int base = 0; base < utotal; base += kStage) {
+                    const int fill = min(kStage, utotal - base);
+                    // asynchronous 16-byte copies global -> shared (LDGSTS): every lane has its kStage / kG records in
+                    // flight at once, nothing passes through registers; the flat index advances monotonically per lane
+#pragma unroll
+                    for (int m = 0; m < kStage / kG; ++m) {
+                        const int q = gl + m * kG;
+                        if (q < fill) {
+                            const int f = base + q;
+                            while (f >= roff[cur + 1]) ++cur;
+                            const unsigned pos = runs[cur].x + (unsigned)(f - roff[cur]);
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + q);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(trecs + pos) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp(gmask);
+#endif
+                    int jloc = -1;      // where in THIS round the smallest float32 distance so far was seen
 #pragma unroll 8
                     for (int j = 0; j < fill; ++j) {
                         const float4 v = stage[j];
                         const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
                         const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        jmin = d2f < f1 ? spos[j] : jmin;
+                        jloc = d2f < f1 ? j : jloc;
                         f2 = fminf(f2, fmaxf(f1, d2f));
                         f1 = fminf(f1, d2f);
                     }
+                    if (jloc >= 0) jmin = flat_to_pos(base + jloc);
                     __syncwarp(gmask);
                 }
                 if (want) resolve(jmin, f1, f2);

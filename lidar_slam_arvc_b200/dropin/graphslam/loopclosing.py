@@ -141,11 +141,22 @@ class LoopClosing():
         return False
 
     def look_for_valid_indexes(self, i, rest_of_candidates):
-        """First candidate u with 1 < |u - i| < 80 and 1.0 m < distance(i, u) < 2.0 m (reference loopclosing.py:131-145)."""
-        for u in rest_of_candidates:
-            if (1 < abs(u - i) < 80) and (1.0 < self.distance(i, u) < 2.0):
-                return u
-        return None
+        """First candidate u with 1 < |u - i| < 80 and 1.0 m < distance(i, u) < 2.0 m (reference loopclosing.py:131-145).
+        The reference tests the candidates one by one (a Python loop calling distance(i, u) per candidate - quadratic in
+        the number of candidates, seconds per invocation on a long trajectory); here the same predicate is evaluated for
+        all of them at once on the positions store_positions() has just read from the same estimate."""
+        rest = np.asarray(rest_of_candidates)
+        if len(rest) == 0:
+            return None
+        if self.positions is None or len(self.positions) <= max(int(rest.max()), int(i)):
+            for u in rest:                                    # no position table (called on its own): the reference's loop
+                if (1 < abs(u - i) < 80) and (1.0 < self.distance(i, u) < 2.0):
+                    return u
+            return None
+        gap = np.abs(rest - i)
+        d = np.sqrt(((self.positions[rest] - self.positions[i]) ** 2).sum(axis=1))
+        ok = np.nonzero((gap > 1) & (gap < 80) & (d > 1.0) & (d < 2.0))[0]
+        return rest[ok[0]] if len(ok) else None
 
     def store_positions(self):
         est = self.graphslam.current_estimate

@@ -143,10 +143,23 @@ class HomogeneousMatrix:
         return np.array([self.array[0, 3], self.array[1, 3], self.array[2, 3], e[0], e[1], e[2]])
 
 
+_NO_REFERENCE = set()
+
+
 def result_type():
-    """The class compute_transformation wraps its result in: the reference's own when available."""
+    """The class compute_transformation wraps its result in: the reference's own when available.  Only the NEGATIVE answer is
+    cached, per sys.path: a failed import is not cached by Python and costs a path search every time (this is called per
+    pose), while a successful one lives in sys.modules - whose current entry must be used, not a remembered class object."""
+    import sys
+    mod = sys.modules.get("artelib.homogeneousmatrix")
+    if mod is not None and hasattr(mod, "HomogeneousMatrix"):
+        return mod.HomogeneousMatrix
+    key = tuple(sys.path)
+    if key in _NO_REFERENCE:
+        return HomogeneousMatrix
     try:
         from artelib.homogeneousmatrix import HomogeneousMatrix as RefH   # noqa: WPS433 (reference tree on sys.path)
         return RefH
     except Exception:
+        _NO_REFERENCE.add(key)
         return HomogeneousMatrix

@@ -60,14 +60,27 @@ class _Pose3:
 
 
 class _Values:
+    """Poses in one preallocated array [capacity, 4, 4] (a run adds thousands, optimize() rewrites all positions at once)."""
+
     def __init__(self):
-        self.poses = []
+        self.buf = np.zeros((1024, 4, 4))
+        self.n = 0
+
+    def append(self, M):
+        if self.n == len(self.buf):
+            self.buf = np.concatenate([self.buf, np.zeros_like(self.buf)])
+        self.buf[self.n] = M
+        self.n += 1
+
+    @property
+    def poses(self):
+        return self.buf[:self.n]
 
     def exists(self, i):
-        return 0 <= i < len(self.poses)
+        return 0 <= i < self.n
 
     def atPose3(self, i):
-        return _Pose3(self.poses[i])
+        return _Pose3(self.buf[i])
 
 
 class PoseGraphStandIn:
@@ -79,45 +92,45 @@ class PoseGraphStandIn:
         self.T0 = np.eye(4) if T0 is None else np.asarray(getattr(T0, "array", T0), dtype=np.float64)
         self.T0_gps = T0_gps if T0_gps is not None else HomogeneousMatrix(np.eye(4))
         self.current_estimate = _Values()
-        self.edges = []
+        self.edges = []                                   # (i, j, 4x4, kind) - what the tests and callers read
+        self._ei, self._ej, self._et, self._ew = [], [], [], []
         self.n_optimizations = 0
 
     def init_graph(self):
-        self.current_estimate.poses = [self.T0.copy()]
+        self.current_estimate = _Values()
+        self.current_estimate.append(self.T0)
 
     def add_initial_estimate(self, atb, k):
-        assert k == len(self.current_estimate.poses)
-        self.current_estimate.poses.append(self.current_estimate.poses[k - 1] @ np.asarray(atb.array))
+        est = self.current_estimate
+        assert k == est.n
+        est.append(est.buf[k - 1] @ np.asarray(atb.array))
 
     def add_edge(self, atb, i, j, kind):
-        self.edges.append((int(i), int(j), np.array(atb.array), kind))
+        A = np.array(atb.array)
+        self.edges.append((int(i), int(j), A, kind))
+        self._ei.append(int(i)); self._ej.append(int(j)); self._et.append(A[:3, 3]); self._ew.append(np.sqrt(self.WEIGHTS.get(kind, 1.0)))
 
     def optimize(self):
         """Positions from one sparse least-squares solve (rotations fixed): sum_e w_e |p_j - p_i - R_i t_ij|^2 + prior on p_0."""
         import scipy.sparse as sp
         import scipy.sparse.linalg as spla
-        n = len(self.current_estimate.poses)
+        P = self.current_estimate.poses
+        n = len(P)
         if n < 2 or not self.edges:
             return
-        R = np.array([P[:3, :3] for P in self.current_estimate.poses])
-        ei = np.array([e[0] for e in self.edges])
-        ej = np.array([e[1] for e in self.edges])
+        ei, ej = np.array(self._ei), np.array(self._ej)
         ok = (ei < n) & (ej < n)
         ei, ej = ei[ok], ej[ok]
-        t = np.array([e[2][:3, 3] for e in self.edges])[ok]
-        w = np.sqrt(np.array([self.WEIGHTS.get(e[3], 1.0) for e in self.edges]))[ok]
+        t = np.array(self._et)[ok]
+        w = np.array(self._ew)[ok]
         m = len(ei)
         rows = np.concatenate([np.arange(m), np.arange(m), [m]])
         cols = np.concatenate([ej, ei, [0]])
         vals = np.concatenate([w, -w, [1e3]])
         A = sp.csr_matrix((vals, (rows, cols)), shape=(m + 1, n))
-        rhs = np.vstack([w[:, None] * np.einsum("kab,kb->ka", R[ei], t), 1e3 * self.current_estimate.poses[0][:3, 3][None]])
-        N = (A.T @ A).tocsc()
-        lu = spla.splu(N)
-        P = lu.solve(A.T @ rhs)
-        for k in range(n):
-            self.current_estimate.poses[k] = self.current_estimate.poses[k].copy()
-            self.current_estimate.poses[k][:3, 3] = P[k]
+        rhs = np.vstack([w[:, None] * np.einsum("kab,kb->ka", P[ei, :3, :3], t), 1e3 * P[0, :3, 3][None]])
+        lu = spla.splu((A.T @ A).tocsc())
+        P[:, :3, 3] = lu.solve(A.T @ rhs)
         self.n_optimizations += 1
 
     def get_solution_transforms_lidar(self):
