@@ -43,9 +43,15 @@ constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
 constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may hold
-constexpr int kUnionScanCap = 384;    // larger unions are split per query (lanes share the records of one query)
+#ifndef ARVC_SCANCAP
+#define ARVC_SCANCAP 1024
+#endif
+constexpr int kUnionScanCap = ARVC_SCANCAP;    // larger unions are split per query (lanes share the records of one query)
 constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * kStack runs fit the stack memory)
-constexpr int kStage = 64;        // records staged in shared memory per group and round
+#ifndef ARVC_STAGE
+#define ARVC_STAGE 64
+#endif
+constexpr int kStage = ARVC_STAGE;        // records staged in shared memory per group and round
 #ifndef ARVC_STAGE_BULK
 #define ARVC_STAGE_BULK 0
 #endif

@@ -163,7 +163,11 @@ __global__ void __launch_bounds__(kNbThreads, ARVC_NBOCC) k_normals_blk(const Sc
         const int z0 = cell_coord(blz - rinf, g.oz, g.inv_c0) >> L, z1 = cell_coord(bhz + rinf, g.oz, g.inv_c0) >> L;
         cnx = x1 - x0 + 1; cny = y1 - y0 + 1; cnz = z1 - z0 + 1;
         const int ncell = cnx * cny * cnz;
-        if (ncell > kNbCells) { block_fallback(); return; }      // a jump of the space-filling curve inside the block
+        if (ncell > kNbCells) {                                 // a jump of the space-filling curve inside the block
+            if ((np.debug & 4) && tid == 0) atomicAdd(&s.counts[15], 1);
+            block_fallback();
+            return;
+        }
         bool valid = false;
         unsigned st = 0, en = 0;
         if (tid < ncell) {

@@ -329,7 +329,7 @@ class Engine:
 
     COUNTER_NAMES = ("n_filtered", "n_points", "error_flags", "grid_cells", "normals_redone", "normals_per_point",
                      "normals_blocks_handed_back", "normals_points_handed_back", "normals_trial_blocks", "dbg_tile_records",
-                     "dbg_neighbours", "dbg_points_one_sweep", "dbg_points_sweep_then_select", "dbg_points_trial", "dbg_records_streamed")
+                     "dbg_neighbours", "dbg_points_one_sweep", "dbg_points_sweep_then_select", "dbg_points_trial", "dbg_records_streamed", "dbg_blocks_too_wide")
 
     def get_counters(self, scan_id):
         """Device counters of a preprocessed scan (see arvc_scan_get_counters) as a dict."""

@@ -37,4 +37,5 @@ if os.environ.get("ARVC_DEBUG_NORMALS"):
     print("   per block: records streamed %.0f, tile %.0f; per point: neighbours %.1f; points: one sweep %d, sweep+select %d, trial %d" % (
         tot["dbg_records_streamed"] / nb, tot["dbg_tile_records"] / nb, tot["dbg_neighbours"] / tot["n_points"],
         tot["dbg_points_one_sweep"], tot["dbg_points_sweep_then_select"], tot["dbg_points_trial"]))
+    print("   blocks handed back: %d too wide (cell box > 256 cells), %d tile overflow" % (tot["dbg_blocks_too_wide"], tot["normals_blocks_handed_back"] - tot["dbg_blocks_too_wide"]))
 eng.close()
