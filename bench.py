@@ -322,8 +322,9 @@ def roofline_dict(prof, passes, n_pts_scans, pass_points, steps, region_ms, meth
         util = {k: v for k, v in tj[key].items() if k.endswith("_pct")}
         if key == "normals" and "dram_bytes_per_scan" in tj[key]:
             traffic = tj[key]["dram_bytes_per_scan"] * len(n_pts_scans)
-        elif key == "icp_pass" and "dram_bytes_per_point_pass" in tj[key]:
-            traffic = tj[key]["dram_bytes_per_point_pass"] * pass_points * steps / n_launch
+        elif key == "icp_pass" and "dram_bytes_per_pair_pass" in tj[key]:
+            # captured at ~63k points per scan: scale by the points this launch searched
+            traffic = tj[key]["dram_bytes_per_pair_pass"] * (pass_points / 63000.0) * steps / n_launch
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "byte_model": model, "launches": n_launch, "kernel_ms_total": tot_ms,
             "kernel_share_of_region": tot_ms / region_ms if region_ms > 0 else None,
@@ -761,13 +762,7 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
             return
         mine = torch.tensor([busy_ms], dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(busy_buf, mine)
-        busy = busy_buf.cpu().numpy()
-        cost = 3.0 + records["passes"].astype(np.float64)
-        for r in range(world):
-            seg = cost[bounds[r]:bounds[r + 1]]
-            if len(seg) and seg.sum() > 0 and busy[r] > 0:
-                cost[bounds[r]:bounds[r + 1]] = seg * (busy[r] / seg.sum())
-        state["bounds"] = sharding.balanced_bounds(cost, world)
+        state["bounds"] = sharding.rebalanced_bounds(records["passes"], bounds, busy_buf.cpu().numpy())
 
     def step(upload, ev=None):
         """One pass over this rank's shard of the global list.  Batch b + 1 is enqueued before batch b is collected, so the
@@ -801,7 +796,7 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
             ticket = eng.icp_batch_async(tg[s0:s1], sr[s0:s1], init[s0:s1].reshape(-1, 4, 4), ip)
             if b == n_batches - 1:
                 ev[1].record(stream)                      # end of this rank's own work of the step (before its last gather)
-            pending.append((ticket, gather.start(ticket, [min(B, max(0, n - b * B)) for n in sizes])))
+            pending.append((ticket, gather.start(ticket, sharding.batch_counts(bounds, b, B))))
             if len(pending) > 1:
                 t, slot = pending.pop(0)
                 parts.append(gather.finish(slot))
@@ -811,13 +806,7 @@ def run_sharded(args, torch, dist, engine, sharding, rank, world, local_rank):
             parts.append(gather.finish(slot))
             eng.icp_batch_finish(t)
         # the gathered batches, back in the order of the global list
-        out = np.zeros(G, dtype=engine.RESULT_DTYPE)
-        for b, part in enumerate(parts):
-            off = 0
-            for r in range(world):
-                n = min(B, max(0, sizes[r] - b * B))
-                out[bounds[r] + b * B: bounds[r] + b * B + n] = part[off:off + n]
-                off += n
+        out = sharding.assemble_global(parts, bounds, B)
         info = {"pairs": hi - lo, "scans": len(my_scans), "bounds": list(bounds), "h2d": int(sum(pinned[int(k)].numel() * 4 for k in my_scans))}
         rebalance(out, bounds, ev[0].elapsed_time(ev[1]))
         return out, info

@@ -140,3 +140,36 @@ def balanced_bounds(costs, world_size):
     for k in range(1, len(b)):                       # monotone, and no shard past the end
         b[k] = min(max(b[k], b[k - 1]), n)
     return b
+
+
+def batch_counts(bounds, b, batch):
+    """Records every rank contributes to device batch `b` (batches of <= `batch` pairs) of its shard [bounds[r], bounds[r+1])."""
+    return [min(batch, max(0, (bounds[r + 1] - bounds[r]) - b * batch)) for r in range(len(bounds) - 1)]
+
+
+def assemble_global(parts, bounds, batch):
+    """The gathered batches (parts[b] = all ranks' records of batch b, in rank order) back in the order of the global list."""
+    world, n = len(bounds) - 1, bounds[-1]
+    out = np.zeros(n, dtype=RESULT_DTYPE)
+    for b, part in enumerate(parts):
+        off = 0
+        for r, c in enumerate(batch_counts(bounds, b, batch)):
+            lo = bounds[r] + b * batch
+            out[lo:lo + c] = part[off:off + c]
+            off += c
+        if off != len(part):
+            raise ValueError("assemble_global: batch %d holds %d records, the bounds say %d" % (b, len(part), off))
+    return out
+
+
+def rebalanced_bounds(passes, bounds, busy_ms, base_cost=3.0):
+    """Run-time load balancer of the sharded pair list.  `passes[k]`: correspondence passes pair k needed in the batch that
+    has just been gathered (every rank holds all records); `busy_ms[r]`: time rank r's GPU spent on its shard.  A pair's
+    cost estimate is (base_cost + passes) x the time its rank needed per such unit; the returned contiguous bounds give
+    every rank the same summed estimate for the NEXT batch (scan locality of the sorted list is kept)."""
+    cost = base_cost + np.asarray(passes, dtype=np.float64)
+    for r in range(len(bounds) - 1):
+        seg = cost[bounds[r]:bounds[r + 1]]
+        if len(seg) and seg.sum() > 0 and busy_ms[r] > 0:
+            cost[bounds[r]:bounds[r + 1]] = seg * (float(busy_ms[r]) / seg.sum())
+    return balanced_bounds(cost, len(bounds) - 1)

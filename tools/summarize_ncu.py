@@ -98,7 +98,7 @@ def traffic(paths, n_scans=9):
                 "dram_pct_of_peak": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
 
     res = {"source": "ncu --set full of tools/prof_target.py %d (%s)" % (n_scans, path.split("/")[-1])}
-    nrm = [r for r in rows[2:] if "k_normals<" in r[idx["Kernel Name"]]]
+    nrm = [r for r in rows[2:] if "k_normals_blk" in r[idx["Kernel Name"]]] or [r for r in rows[2:] if "k_normals<" in r[idx["Kernel Name"]]]
     srch = [r for r in rows[2:] if "k_icp_search" in r[idx["Kernel Name"]]]
     if nrm:
         r = nrm[0]
