@@ -20,6 +20,8 @@ class ScanLoader:
         self.executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="arvc-readahead")
         self.pending = {}                # filename -> Future of (array, pinned handle)
         self.stats = {"read_ahead_hits": 0, "reads": 0}
+        self.prewarmed = False
+        self.prewarm_buffers = 8
 
     def _read(self, filename):
         handle = [None]
@@ -29,6 +31,14 @@ class ScanLoader:
             return arr
 
         xyz = read_pcd_xyz(filename, alloc=alloc if self.pool is not None else None)
+        if self.pool is not None and not self.prewarmed and handle[0] is not None:
+            # cudaMallocHost waits for the GPU to go idle: allocating a staging buffer while a registration batch runs would
+            # stall the very load it is meant to overlap.  The scans of a sequence have one size, so a handful of buffers of
+            # that size are allocated now, with the first scan, and recycled from then on.
+            self.prewarmed = True
+            spare = [self.pool.empty(len(xyz) + len(xyz) // 8, xyz.dtype)[1] for _ in range(self.prewarm_buffers)]
+            for h in spare:
+                self.pool.release(h)
         return xyz, handle[0]
 
     def prefetch(self, filename):
