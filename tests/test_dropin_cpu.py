@@ -46,6 +46,33 @@ def test_pcd_roundtrip(tmp_path):
     assert lzf_decompress(stream, 3 + 6 + 1 + 12) == b"abcabcabcZ" + b"Z" * 12
     with pytest.raises(ValueError):
         lzf_decompress(bytes([(1 << 5) | 0, 9]), 3)            # back reference before the start of the output
+    # PCL-style padding: repeated fields named "_" with COUNT > 1 (o3d.io.read_point_cloud reads such files)
+    fn = str(tmp_path / "d.pcd")
+    rec = np.zeros(7, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("p0", "u1", (4,)), ("intensity", "<f4"), ("p1", "u1", (12,))])
+    rec["x"], rec["y"], rec["z"], rec["intensity"] = np.arange(7), -np.arange(7), 0.5, 9.0
+    with open(fn, "wb") as f:
+        f.write(b"VERSION 0.7\nFIELDS x y z _ intensity _\nSIZE 4 4 4 1 4 1\nTYPE F F F U F U\nCOUNT 1 1 1 4 1 12\nWIDTH 7\nHEIGHT 1\nPOINTS 7\nDATA binary\n")
+        f.write(rec.tobytes())
+    back = pcd.read_pcd_xyz(fn)
+    assert back.dtype == np.float32
+    np.testing.assert_array_equal(back, np.stack([rec["x"], rec["y"], rec["z"]], axis=1))
+    # an unsupported field type is reported, not a bare KeyError
+    with open(fn, "wb") as f:
+        f.write(b"VERSION 0.7\nFIELDS x y z w\nSIZE 4 4 4 3\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 15)
+    with pytest.raises(ValueError, match="unsupported PCD field type"):
+        pcd.read_pcd_xyz(fn)
+    # the allocator hook (page-locked staging on the load path): same values, caller-supplied memory
+    made = []
+
+    def alloc(n_rows, dtype):
+        made.append(np.empty((n_rows, 3), dtype=dtype))
+        return made[-1]
+    for binary, compressed in ((True, False), (False, False), (True, True)):
+        fn = str(tmp_path / ("h_%d_%d.pcd" % (binary, compressed)))
+        pcd.write_pcd_xyz(fn, xyz, binary=binary, compressed=compressed)
+        out = pcd.read_pcd_xyz(fn, alloc=alloc)
+        assert out is made[-1]
+        np.testing.assert_array_equal(out, xyz)
     empty = str(tmp_path / "e.pcd")
     pcd.write_pcd_xyz(empty, np.zeros((0, 3)))
     assert pcd.read_pcd_xyz(empty).shape == (0, 3)
