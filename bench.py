@@ -290,6 +290,9 @@ def split_profile(prof_raw):
             passes[k[-2:]] = round(v[1] / v[0], 4)
             c, t = prof.get("icp_pass", (0, 0.0))
             prof["icp_pass"] = (c + v[0], t + v[1])
+        elif k.startswith("icp_far_"):
+            c, t = prof.get("icp_far", (0, 0.0))
+            prof["icp_far"] = (c + v[0], t + v[1])
         else:
             prof[k] = v
     return prof, passes

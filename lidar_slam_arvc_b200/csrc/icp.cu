@@ -1135,10 +1135,13 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
     // far queries: a few per cent of the points; 296 blocks x 8 groups per pair stride over the pair's far list
     const dim3 gfar(kFarBlocks * mult, n_pairs_grid);
-    if (combos_mask & 1) E.kernel("icp_far", (const void*)k_icp_far<false, false>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 2) E.kernel("icp_far", (const void*)k_icp_far<false, true>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 4) E.kernel("icp_far", (const void*)k_icp_far<true, false>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 8) E.kernel("icp_far", (const void*)k_icp_far<true, true>, gfar, dim3(kIcpBlock), args);
+    static char far_names[64][16];
+    snprintf(far_names[pass < 63 ? pass : 63], 16, "icp_far_%02d", pass < 63 ? pass : 63);
+    const char* fn = far_names[pass < 63 ? pass : 63];
+    if (combos_mask & 1) E.kernel(fn, (const void*)k_icp_far<false, false>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel(fn, (const void*)k_icp_far<false, true>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel(fn, (const void*)k_icp_far<true, false>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel(fn, (const void*)k_icp_far<true, true>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 1) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), args);

@@ -24,7 +24,7 @@ for rep in range(4):
     r = eng.icp_batch(ids[:-1], ids[1:], init, ip)
     prof = eng.profile_report()
     eng.profile_enable(False)
-    t = {"search": sum(v[1] for k, v in prof.items() if k.startswith("icp_pass")), "far": prof["icp_far"][1], "select": prof["icp_select"][1],
+    t = {"search": sum(v[1] for k, v in prof.items() if k.startswith("icp_pass")), "far": sum(v[1] for k, v in prof.items() if k.startswith("icp_far")), "select": prof["icp_select"][1],
          "accum": prof["icp_accum"][1], "finish": prof["icp_finish"][1]}
     if best is None or sum(t.values()) < sum(best.values()):
         best = t
