@@ -911,7 +911,10 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
     return ARVC_OK;
 }
 
-static void icp_release(arvc_ctx* ctx, PendingBatch& pb) {
+// `abandoned`: the batch failed while it was being enqueued - copies from its staging buffer may still be queued, so the
+// stream is drained before the buffers go back to the pools (a later batch must not overwrite them in flight).
+static void icp_release(arvc_ctx* ctx, PendingBatch& pb, bool abandoned = false) {
+    if (abandoned) cudaStreamSynchronize(ctx->L.stream);
     if (pb.slab) { ctx->dev_put(pb.slab, pb.slab_bytes); pb.slab = nullptr; }
     ctx->pinned_put(pb.h_states, pb.h_bytes); pb.h_states = nullptr;
     ctx->pinned_put(pb.h_stage, pb.h_stage_bytes); pb.h_stage = nullptr;
@@ -957,7 +960,7 @@ int arvc_icp_batch_async(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, con
     if (!ctx || !ticket) return ARVC_E_ARG;
     PendingBatch pb;
     const int rc = icp_enqueue(ctx, n_pairs, tgt_ids, src_ids, init_T, p, false, pb, nullptr, nullptr, nullptr);
-    if (rc) { icp_release(ctx, pb); return rc; }
+    if (rc) { icp_release(ctx, pb, true); return rc; }
     *ticket = ctx->next_ticket++;
     ctx->pending[*ticket] = std::move(pb);
     return ARVC_OK;
@@ -1008,7 +1011,7 @@ int arvc_icp_trace(arvc_ctx* ctx, int64_t tgt_id, int64_t src_id, const double* 
     double* d_st = nullptr;
     int cap = 0;
     int rc = icp_enqueue(ctx, 1, &tgt_id, &src_id, init_T, p, true, pb, &d_ct, &d_st, &cap);
-    if (rc) { icp_release(ctx, pb); return rc; }
+    if (rc) { icp_release(ctx, pb, true); return rc; }
     const int passes_max = p->max_iter + 1;
     std::vector<int> hct((size_t)cap * passes_max);
     std::vector<double> hst((size_t)passes_max * 18);
