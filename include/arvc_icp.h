@@ -98,6 +98,13 @@ typedef struct arvc_preprocess_params {
 /* KeyFrame.pre_process (keyframe.py:113-162) for a batch of uploaded scans: filter -> [voxel] -> spatial
  * sort + hash grid -> [normals].  Queued on the context stream; no host synchronisation. */
 int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p);
+/* The same work for scans the caller will need NEXT, queued on a second compute stream so that it overlaps what is already
+ * queued on the context stream - in the reference's loop (run_scanmatcher.py:196-213: load i+1, pre_process i+1,
+ * compute_transformation(i, i+1), one pair per call) the scan i+2 is preprocessed while the pair (i, i+1) is registered.
+ * Call it between arvc_icp_batch_async and arvc_icp_batch_finish.  Every later call on the context is ordered after it;
+ * a later arvc_scan_preprocess with the same parameters finds the scan done.  Scans that already hold preprocessed
+ * state are handled as by arvc_scan_preprocess (on the context stream). */
+int arvc_scan_preprocess_ahead(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p);
 
 /* Sizes after preprocessing (synchronises): raw, after filter, final cloud size; has_normals. */
 int arvc_scan_info(arvc_ctx* ctx, int64_t scan_id, int* n_raw, int* n_filtered, int* n_points, int* has_normals);

@@ -72,6 +72,20 @@ struct arvc_ctx {
     int device = 0;
     Launcher L;
     cudaStream_t copy_stream = nullptr;   // host -> device uploads, so that they overlap the kernels of earlier scans
+    // Look-ahead preprocessing (arvc_scan_preprocess_ahead): a second compute stream with a scratch block of its own, so
+    // that the next scan of a sequential caller is preprocessed while the registration enqueued before it still runs.
+    // `ahead_ev` marks the end of the last look-ahead job; the main stream waits for it at the next entry point.
+    cudaStream_t ahead_stream = nullptr;
+    cudaEvent_t ahead_ev = nullptr;
+    bool ahead_pending = false;
+    void* ahead_scratch = nullptr;
+    size_t ahead_scratch_bytes = 0;
+    int enter() {                         // every entry point but the look-ahead one: select the device, join the side stream
+        const cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) return (int)e;
+        if (ahead_pending) { cudaStreamWaitEvent(L.stream, ahead_ev, 0); ahead_pending = false; }
+        return 0;
+    }
     std::string error;
     std::unordered_map<int64_t, std::unique_ptr<Scan>> scans;
     std::map<uint64_t, PendingBatch> pending;
@@ -191,7 +205,7 @@ int bits_for(double cells) {
 int upload(arvc_ctx* ctx, int64_t id, const void* xyz, int n, bool f64) {
     if (!ctx) return ARVC_E_ARG;
     if (n < 0 || (n > 0 && !xyz)) return ctx->fail(ARVC_E_ARG, "scan_upload: bad pointer/size");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     Scan* old = ctx->find(id);
     if (old) { release_scan(ctx, old); ctx->scans.erase(id); }
     auto s = std::make_unique<Scan>();
@@ -276,8 +290,14 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ARVC_E_CUDA; }
     auto ctx = new arvc_ctx();
     ctx->device = device;
+    // the look-ahead stream yields to the context stream: blocks of a registration in flight (short, latency-bound
+    // kernels) are scheduled before the blocks of the next scan's preprocessing, which only fills the gaps
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->L.stream, cudaStreamNonBlocking, prio_greatest);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->ahead_stream, cudaStreamNonBlocking, prio_least);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ahead_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ARVC_E_CUDA; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -299,8 +319,10 @@ int arvc_ctx_set_option(arvc_ctx* ctx, const char* name, int value) {
 
 void arvc_ctx_destroy(arvc_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    ctx->enter();
+    cudaStreamSynchronize(ctx->ahead_stream);
     cudaStreamSynchronize(ctx->L.stream);
+    if (ctx->ahead_scratch) cudaFreeAsync(ctx->ahead_scratch, ctx->L.stream);
     icp_graphs_destroy(ctx->icp_graphs);
     for (auto& df : ctx->dev_free) cudaFreeAsync(df.second, ctx->L.stream);
     for (auto& kv : ctx->pending) {
@@ -317,7 +339,9 @@ void arvc_ctx_destroy(arvc_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->L.stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->ahead_stream);
     cudaStreamDestroy(ctx->L.stream);
+    if (ctx->ahead_ev) cudaEventDestroy(ctx->ahead_ev);
     delete ctx;
 }
 
@@ -326,6 +350,7 @@ const char* arvc_last_error(const arvc_ctx* ctx) { return ctx ? ctx->error.c_str
 int arvc_sync(arvc_ctx* ctx) {
     if (!ctx) return ARVC_E_ARG;
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->ahead_stream));
     CK(cudaStreamSynchronize(ctx->L.stream));
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     return ARVC_OK;
@@ -346,7 +371,7 @@ int arvc_profile_enable(arvc_ctx* ctx, int on) {
 
 int arvc_profile_report(arvc_ctx* ctx, char* buf, size_t cap) {
     if (!ctx || !buf || cap == 0) return ARVC_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     CK(cudaStreamSynchronize(ctx->L.stream));
     std::map<std::string, std::pair<long long, double>> agg;
     for (auto& r : ctx->L.recs) {
@@ -390,16 +415,31 @@ int arvc_scan_free(arvc_ctx* ctx, int64_t scan_id) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s) return ARVC_OK;
-    cudaSetDevice(ctx->device);
+    ctx->enter();
     release_scan(ctx, s);
     ctx->scans.erase(scan_id);
     return ARVC_OK;
 }
 
-int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p) {
+namespace {
+// arvc_scan_preprocess (ahead = false) and arvc_scan_preprocess_ahead (ahead = true: same work on the look-ahead stream)
+int preprocess_impl(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p, bool ahead) {
     if (!ctx) return ARVC_E_ARG;
     if (n_scans < 0 || (n_scans > 0 && !scan_ids) || !p) return ctx->fail(ARVC_E_ARG, "scan_preprocess: bad arguments");
-    CK(cudaSetDevice(ctx->device));
+    if (ahead) {
+        // only scans without device state of their own may go ahead: nothing on the main stream can be using them
+        for (int i = 0; i < n_scans; ++i) {
+            const Scan* s = ctx->find(scan_ids[i]);
+            if (s && (s->slab || s->d_dev)) ahead = false;
+        }
+    }
+    if (ahead) CK(cudaSetDevice(ctx->device)); else CK((cudaError_t)ctx->enter());
+    // every launch, copy and allocation below goes through ctx->L.stream: the look-ahead variant swaps the stream in
+    struct StreamSwap {
+        arvc_ctx* c; cudaStream_t saved; bool on;
+        StreamSwap(arvc_ctx* c_, bool on_) : c(c_), saved(c_->L.stream), on(on_) { if (on) c->L.stream = c->ahead_stream; }
+        ~StreamSwap() { if (on) c->L.stream = saved; }
+    } swap_guard(ctx, ahead);
     const bool voxel_on = p->voxel_size > 0.0;          // NaN and <= 0 mean "voxel_size is None"
     const bool want_normals = p->want_normals != 0;
     if (!(p->max_radius2 > 0) || !std::isfinite(p->max_radius2) || !std::isfinite(p->min_height) || !std::isfinite(p->max_height) ||
@@ -484,7 +524,19 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
     }
     const size_t scratch_bytes = scratch_plan.off + align_up(sizeof(ScanDev) * todo.size());
     size_t scratch_cap = 0;
-    void* scratch = ctx->dev_get(scratch_bytes, &scratch_cap);
+    void* scratch = nullptr;
+    if (ahead) {      // the side stream's own block: the recycled blocks of dev_get are ordered by the main stream only
+        if (ctx->ahead_scratch_bytes < scratch_bytes) {
+            if (ctx->ahead_scratch) cudaFreeAsync(ctx->ahead_scratch, ctx->L.stream);
+            ctx->ahead_scratch = nullptr;
+            ctx->ahead_scratch_bytes = 0;
+            const size_t cap = scratch_bytes + scratch_bytes / 4;
+            if (cudaMallocAsync(&ctx->ahead_scratch, cap, ctx->L.stream) == cudaSuccess) ctx->ahead_scratch_bytes = cap;
+        }
+        scratch = ctx->ahead_scratch;
+    } else {
+        scratch = ctx->dev_get(scratch_bytes, &scratch_cap);
+    }
     if (!scratch) return ctx->fail(ARVC_E_NOMEM, "scan_preprocess: device allocation failed");
     SlabPlanner sp;
     sp.base = reinterpret_cast<char*>(scratch);
@@ -511,9 +563,23 @@ int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, co
         s->voxel_on = voxel_on;
         s->params = *p;
     }
-    ctx->dev_put(scratch, scratch_cap);
+    if (ahead) {
+        CK(cudaEventRecord(ctx->ahead_ev, ctx->L.stream));
+        ctx->ahead_pending = true;
+    } else {
+        ctx->dev_put(scratch, scratch_cap);
+    }
     if (ctx->L.err != cudaSuccess) return ctx->cuda_fail(ctx->L.err, "kernel launch");
     return ARVC_OK;
+}
+}  // namespace
+
+int arvc_scan_preprocess(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p) {
+    return preprocess_impl(ctx, n_scans, scan_ids, p, false);
+}
+
+int arvc_scan_preprocess_ahead(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const arvc_preprocess_params* p) {
+    return preprocess_impl(ctx, n_scans, scan_ids, p, true);
 }
 
 static int fetch_counts(arvc_ctx* ctx, Scan* s, int* counts) {
@@ -528,7 +594,7 @@ int arvc_scan_info(arvc_ctx* ctx, int64_t scan_id, int* n_raw, int* n_filtered, 
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s) return ctx->fail(ARVC_E_STATE, "scan_info: unknown scan id");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     if (n_raw) *n_raw = s->n_raw;
     if (has_normals) *has_normals = s->has_normals ? 1 : 0;
     if (!s->preprocessed) {
@@ -549,7 +615,7 @@ int arvc_scan_get_points(arvc_ctx* ctx, int64_t scan_id, double* xyz, double* no
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_get_points: scan not preprocessed");
     if (normals && !s->has_normals) return ctx->fail(ARVC_E_STATE, "scan_get_points: no normals (point-to-point preprocessing)");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     int c[CNT_WORDS];
     const int rc = fetch_counts(ctx, s, c);
     if (rc) return rc;
@@ -583,7 +649,7 @@ int arvc_map_build(arvc_ctx* ctx, int n_scans, const int64_t* scan_ids, const do
     if (n_scans > 32768) return ctx->fail(ARVC_E_ARG, "map_build: at most 32768 keyframes per call (split the batch)");
     offsets_out[0] = 0;
     if (n_scans == 0) return ARVC_OK;
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     std::vector<int64_t> uniq(scan_ids, scan_ids + n_scans);          // a keyframe may appear more than once in a map
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
@@ -640,7 +706,7 @@ int arvc_scan_fit_plane(arvc_ctx* ctx, int64_t scan_id, double max_z, double dis
     if (!plane_out || iterations < 1 || iterations > 65535 || !(dist_threshold > 0)) return ctx->fail(ARVC_E_ARG, "scan_fit_plane: bad arguments");
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_fit_plane: scan not preprocessed");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     const size_t cap = (size_t)std::max(s->dev.cap, 1);
     const size_t orig_b = align_up(sizeof(double) * 3 * cap), score_b = align_up(sizeof(int) * (size_t)iterations), res_b = align_up(sizeof(double) * 5);
     size_t got = 0;
@@ -668,7 +734,7 @@ int arvc_scan_split_plane(arvc_ctx* ctx, int64_t src_id, const double* plane, do
     if (!s || !s->preprocessed) return ctx->fail(ARVC_E_STATE, "scan_split_plane: scan not preprocessed");
     const double norm = std::sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);    // np.sqrt(a*a + b*b + c*c)
     if (!(norm > 0)) return ctx->fail(ARVC_E_ARG, "scan_split_plane: degenerate plane");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     for (int64_t id : {near_id, far_id}) {
         Scan* old = ctx->find(id);
         if (old) { release_scan(ctx, old); ctx->scans.erase(id); }
@@ -713,7 +779,7 @@ int arvc_scan_get_filter_indices(arvc_ctx* ctx, int64_t scan_id, int32_t* raw_in
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed || !raw_index) return ctx->fail(ARVC_E_STATE, "scan_get_filter_indices: scan not preprocessed");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     int c[CNT_WORDS];
     const int rc = fetch_counts(ctx, s, c);
     if (rc) return rc;
@@ -728,7 +794,7 @@ int arvc_scan_get_voxels(arvc_ctx* ctx, int64_t scan_id, int32_t* keys, int32_t*
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed || !s->voxel_on) return ctx->fail(ARVC_E_STATE, "scan_get_voxels: scan not preprocessed with a voxel size");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     int c[CNT_WORDS];
     const int rc = fetch_counts(ctx, s, c);
     if (rc) return rc;
@@ -745,7 +811,7 @@ int arvc_scan_get_nn_counts(arvc_ctx* ctx, int64_t scan_id, int32_t* nn_count) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed || !s->has_normals || !nn_count) return ctx->fail(ARVC_E_STATE, "scan_get_nn_counts: no normals");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     int c[CNT_WORDS];
     const int rc = fetch_counts(ctx, s, c);
     if (rc) return rc;
@@ -769,7 +835,7 @@ int arvc_scan_get_neighbors(arvc_ctx* ctx, int64_t scan_id, int n_query, const i
     if (!s || !s->preprocessed || !s->has_normals) return ctx->fail(ARVC_E_STATE, "scan_get_neighbors: no normals");
     if (!s->dev.tap_idx) return ctx->fail(ARVC_E_STATE, "scan_get_neighbors: preprocess the scan with the context option \"normals_tap\" set");
     if (n_query < 0 || (n_query > 0 && (!point_ids || !out_idx || !out_cnt))) return ctx->fail(ARVC_E_ARG, "scan_get_neighbors: bad arguments");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     int c[CNT_WORDS];
     const int rc = fetch_counts(ctx, s, c);
     if (rc) return rc;
@@ -803,7 +869,7 @@ int arvc_scan_get_counters(arvc_ctx* ctx, int64_t scan_id, int32_t* counters) {
     if (!ctx) return ARVC_E_ARG;
     Scan* s = ctx->find(scan_id);
     if (!s || !s->preprocessed || !counters) return ctx->fail(ARVC_E_STATE, "scan_get_counters: scan not preprocessed");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     static_assert(CNT_WORDS == 16, "arvc_scan_get_counters documents 16 words");
     CK(cudaMemcpyAsync(counters, s->dev.counts, sizeof(int) * CNT_WORDS, cudaMemcpyDeviceToHost, ctx->L.stream));
     CK(cudaStreamSynchronize(ctx->L.stream));
@@ -818,7 +884,7 @@ static int icp_enqueue(arvc_ctx* ctx, int n_pairs, const int64_t* tgt_ids, const
     if (p->method != ARVC_P2P && p->method != ARVC_P2PLANE) return ctx->fail(ARVC_E_ARG, "icp: unknown method");
     if (p->max_iter < 0) return ctx->fail(ARVC_E_ARG, "icp: max_iter < 0");
     if (n_pairs > 32768) return ctx->fail(ARVC_E_ARG, "icp: at most 32768 pairs per call (split the batch)");
-    CK(cudaSetDevice(ctx->device));
+    CK((cudaError_t)ctx->enter());
     pb.n_pairs = n_pairs;
     if (n_pairs == 0) return ARVC_OK;
     int combos = 0, src_cap_max = 1;

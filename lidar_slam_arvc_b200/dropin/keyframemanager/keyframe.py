@@ -96,8 +96,20 @@ class KeyFrame():
         print('Reading pointcloud: ', filename)
         if self._on_device and self._loaded_from == filename:
             return
-        xyz, handle = runtime.get_loader().fetch(filename)
-        self.set_points(xyz, _pinned_handle=handle)
+        staged = runtime.get_loader().take_staged(filename)
+        if staged is not None:
+            # uploaded and preprocessed ahead, while the previous pair was being registered: adopt that device scan
+            self._release_staging()
+            if self._on_device:
+                runtime.get_engine().free(self._scan_id)
+            self._scan_id, xyz, self._pinned_handle = staged
+            self.pointcloud = PointCloud(xyz)
+            self._on_device = True
+            self._preprocessed_on_device = False
+            self._filtered_cache = None
+        else:
+            xyz, handle = runtime.get_loader().fetch(filename)
+            self.set_points(xyz, _pinned_handle=handle)
         self._loaded_from = filename
 
     def set_points(self, xyz, _pinned_handle=None):
@@ -220,9 +232,11 @@ class KeyFrame():
 
     def preprocess_icp_point_point(self):
         self._preprocess(self._params(False))
+        runtime.get_loader().ahead_params = self._last_params      # what a scan read ahead will be preprocessed with
 
     def preprocess_icp_point_plane(self):
         self._preprocess(self._params(True))
+        runtime.get_loader().ahead_params = self._last_params
 
     def preprocess_icp2planes(self):
         """keyframe.py:164-189: filter -> [voxel] -> normals, ground-plane model, split into the points within 0.4 m of
@@ -230,6 +244,7 @@ class KeyFrame():
         Like the reference, the plane is recomputed on every call (keyframe.py:173) - unless the caller pinned one in
         `fixed_plane_model` (the reference hints at a fixed model, keyframe.py:436)."""
         self._preprocess(self._params(True))
+        runtime.get_loader().ahead_params = self._last_params      # the first step of the next keyframe can go ahead too
         self.plane_model = np.asarray(self.fixed_plane_model, dtype=np.float64) if self.fixed_plane_model is not None else self.calculate_plane()
         self.segment_plane(self.plane_model, _download=False)
         eng = runtime.get_engine()
@@ -288,7 +303,12 @@ class KeyFrame():
         eng = runtime.get_engine()
         ip = eng.make_icp_params(method, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
                                  ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)
-        rec = eng.icp_batch([self._scan_id], [other._scan_id], np.asarray(initial_transform, dtype=np.float64)[None], ip)[0]
+        # enqueue, then - while the device iterates - stage the scan the caller will ask for next, then wait
+        ticket = eng.icp_batch_async([self._scan_id], [other._scan_id], np.asarray(initial_transform, dtype=np.float64)[None], ip)
+        try:
+            runtime.get_loader().stage_ahead(runtime.new_scan_id)
+        finally:
+            rec = eng.icp_batch_finish(ticket)[0]
         self.last_result = rec
         print('Registration result: fitness=%.6e, inlier_rmse=%.6e, correspondence_set size=%d, iterations=%d'
               % (rec["fitness"], rec["rmse"], rec["n_corr"], rec["updates"]))
@@ -306,8 +326,12 @@ class KeyFrame():
         ip = eng.make_icp_params(P2PLANE, ICP_PARAMETERS.distance_threshold, ICP_PARAMETERS.relative_fitness,
                                  ICP_PARAMETERS.relative_rmse, ICP_PARAMETERS.max_iteration)
         init = np.asarray(initial_transform, dtype=np.float64)
-        rec = eng.icp_batch([self._scan_id_ground, self._scan_id_non_ground], [other._scan_id_ground, other._scan_id_non_ground],
-                            np.stack([init, init]), ip)
+        ticket = eng.icp_batch_async([self._scan_id_ground, self._scan_id_non_ground],
+                                     [other._scan_id_ground, other._scan_id_non_ground], np.stack([init, init]), ip)
+        try:
+            runtime.get_loader().stage_ahead(runtime.new_scan_id)
+        finally:
+            rec = eng.icp_batch_finish(ticket)
         self.last_result = rec[1]
         return merge_two_planes(np.array(rec[0]["T"]), np.array(rec[1]["T"]))
 

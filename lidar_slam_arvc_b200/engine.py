@@ -16,7 +16,7 @@ P2P, P2PLANE = 0, 1
 # every symbol include/arvc_icp.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
     "arvc_ctx_create", "arvc_ctx_destroy", "arvc_last_error", "arvc_sync", "arvc_stream", "arvc_version",
-    "arvc_kernel_launches", "arvc_scan_upload_f32", "arvc_scan_upload_f64", "arvc_scan_free", "arvc_scan_preprocess",
+    "arvc_kernel_launches", "arvc_scan_upload_f32", "arvc_scan_upload_f64", "arvc_scan_free", "arvc_scan_preprocess", "arvc_scan_preprocess_ahead",
     "arvc_scan_info", "arvc_scan_get_points", "arvc_scan_get_filter_indices", "arvc_scan_get_voxels",
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
@@ -75,6 +75,7 @@ def load_library():
     lib.arvc_scan_free.argtypes = [vp, c.c_int64]
     lib.arvc_scan_wait_upload.argtypes = [vp, c.c_int64]
     lib.arvc_scan_preprocess.argtypes = [vp, c.c_int, i64p, c.POINTER(PreprocessParams)]
+    lib.arvc_scan_preprocess_ahead.argtypes = [vp, c.c_int, i64p, c.POINTER(PreprocessParams)]
     lib.arvc_scan_info.argtypes = [vp, c.c_int64, ip, ip, ip, ip]
     lib.arvc_scan_get_points.argtypes = [vp, c.c_int64, dp, dp]
     lib.arvc_scan_get_filter_indices.argtypes = [vp, c.c_int64, ip]
@@ -256,6 +257,11 @@ class Engine:
     def preprocess(self, scan_ids, params):
         ids = np.ascontiguousarray(scan_ids, dtype=np.int64).reshape(-1)
         self._ck(self.lib.arvc_scan_preprocess(self.h, len(ids), _i64p(ids), ctypes.byref(params)))
+
+    def preprocess_ahead(self, scan_ids, params):
+        """preprocess() of scans needed next, on the engine's look-ahead stream (overlaps a registration in flight)."""
+        ids = np.ascontiguousarray(scan_ids, dtype=np.int64).reshape(-1)
+        self._ck(self.lib.arvc_scan_preprocess_ahead(self.h, len(ids), _i64p(ids), ctypes.byref(params)))
 
     def info(self, scan_id):
         v = [ctypes.c_int32() for _ in range(4)]

@@ -6,6 +6,12 @@ follows is a true asynchronous copy on the engine's copy stream, and it reads AH
 pair (i, i + 1) - a synchronous call - one helper thread already reads and parses the file of scan i + 2.  The
 reference's loop (run_scanmatcher.py:196-213) calls load_pointcloud(i + 2) next, which then only enqueues the copy.
 With an engine that has no pinned pool (the CPU test double) the loader degrades to plain numpy arrays.
+
+The read-ahead goes one step further when the caller registers one pair per call: `stage_ahead()` - called by the
+registration between enqueueing its batch and waiting for it - uploads the scan that was read ahead under a fresh scan
+id and preprocesses it on the engine's look-ahead stream (`arvc_scan_preprocess_ahead`), with the parameters of the
+caller's last pre_process().  The keyframe that loads that file next adopts the staged scan: its own pre_process() then
+finds the work done, and the GPU has spent the registration's latency-bound passes on something useful.
 """
 import os
 from concurrent.futures import ThreadPoolExecutor
@@ -19,7 +25,9 @@ class ScanLoader:
         self.pool = getattr(engine, "pinned", None)
         self.executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="arvc-readahead")
         self.pending = {}                # filename -> Future of (array, pinned handle)
-        self.stats = {"read_ahead_hits": 0, "reads": 0}
+        self.staged = {}                 # filename -> (scan id, array, pinned handle): uploaded + preprocessed ahead
+        self.ahead_params = None         # parameters of the caller's last plain pre_process(); None = do not stage
+        self.stats = {"read_ahead_hits": 0, "reads": 0, "staged": 0, "staged_hits": 0}
         self.prewarmed = False
         self.prewarm_buffers = 8
 
@@ -50,6 +58,41 @@ class ScanLoader:
             self.release(self.pending.pop(old).result()[1])
         self.pending[filename] = self.executor.submit(self._read, filename)
 
+    def stage_ahead(self, new_scan_id, wait_s=0.0005):
+        """Upload + preprocess (look-ahead stream) what has been read ahead.  `new_scan_id`: allocator of engine scan ids."""
+        if self.ahead_params is None or not self.pending or not hasattr(self.engine, "preprocess_ahead"):
+            return
+        for filename in list(self.pending):
+            fut = self.pending[filename]
+            try:
+                xyz, handle = fut.result(timeout=wait_s)      # normally long done: it was started before the pre_process
+            except Exception:
+                continue                                      # still reading (or failed): the ordinary path will handle it
+            del self.pending[filename]
+            while len(self.staged) >= 2:                      # a caller that changed its mind must not pile up scans
+                self._drop_staged(next(iter(self.staged)))
+            sid = new_scan_id()
+            self.engine.upload(sid, xyz)
+            self.engine.preprocess_ahead([sid], self.ahead_params)
+            self.staged[filename] = (sid, xyz, handle)
+            self.stats["staged"] += 1
+
+    def take_staged(self, filename):
+        """(scan id, xyz, pinned handle) of a scan staged by stage_ahead(), or None; the caller owns all three afterwards."""
+        st = self.staged.pop(filename, None)
+        if st is not None:
+            self.stats["reads"] += 1
+            self.stats["read_ahead_hits"] += 1
+            self.stats["staged_hits"] += 1
+        return st
+
+    def _drop_staged(self, filename):
+        sid, _, handle = self.staged.pop(filename)
+        if handle is not None:
+            self.engine.wait_upload(sid)
+        self.engine.free(sid)
+        self.release(handle)
+
     def fetch(self, filename):
         """(xyz, pinned handle or None): the read-ahead result when there is one, else a synchronous read."""
         self.stats["reads"] += 1
@@ -67,4 +110,9 @@ class ScanLoader:
         for fut in self.pending.values():
             self.release(fut.result()[1])
         self.pending = {}
+        for filename in list(self.staged):
+            try:
+                self._drop_staged(filename)
+            except Exception:
+                self.staged.pop(filename, None)
         self.executor.shutdown(wait=True)

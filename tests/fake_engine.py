@@ -17,19 +17,31 @@ class OracleEngine:
     def __init__(self):
         self.raw = {}
         self.pre = {}
+        self.pre_params = {}
         self.calls = []
 
     def upload(self, scan_id, xyz):
         self.raw[int(scan_id)] = np.asarray(xyz)
         self.pre.pop(int(scan_id), None)
+        self.pre_params.pop(int(scan_id), None)
 
     def free(self, scan_id):
         self.raw.pop(int(scan_id), None)
         self.pre.pop(int(scan_id), None)
+        self.pre_params.pop(int(scan_id), None)
 
-    def preprocess(self, scan_ids, p):
-        self.calls.append(("preprocess", len(np.atleast_1d(scan_ids))))
+    def preprocess_ahead(self, scan_ids, p):
+        """The look-ahead variant: same results; the double only records that it was used."""
+        self.calls.append(("preprocess_ahead", len(np.atleast_1d(scan_ids))))
+        self.preprocess(scan_ids, p, _count=False)
+
+    def preprocess(self, scan_ids, p, _count=True):
+        if _count:
+            self.calls.append(("preprocess", len(np.atleast_1d(scan_ids))))
         for k in np.atleast_1d(scan_ids):
+            if int(k) in self.pre and self.pre_params.get(int(k)) == bytes(p):
+                continue                                  # like the engine: same scan, same parameters -> nothing to do
+            self.pre_params[int(k)] = bytes(p)
             pts = self.raw[int(k)].astype(np.float64)
             d = pts[:, 0] ** 2 + pts[:, 1] ** 2
             with np.errstate(invalid="ignore"):

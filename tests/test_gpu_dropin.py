@@ -237,6 +237,95 @@ def test_load_path_pinned_read_ahead_overlaps_registration(kfm_module, tmp_path)
         km.unload_pointcloud(i)
 
 
+def test_sequential_loop_preprocesses_the_next_scan_ahead(kfm_module, tmp_path):
+    """The one-pair-per-call loop of run_scanmatcher.py:196-213 at 64 beams: while pair (i, i+1) is registered, scan i+2 is
+    uploaded and preprocessed on the engine's look-ahead stream (arvc_scan_preprocess_ahead) and adopted by the keyframe
+    that loads it next.  Same kernels on the same data: clouds, normals and transforms are BIT-identical to a run without
+    the look-ahead, and the staged scans are all used and all released."""
+    seq = synth.Sequence(6, synth.OS1_64, start=30.0)
+    d = str(tmp_path / "euroc")
+    times = euroc_synth.write_euroc_tree(d, seq)
+    odo = [HomogeneousMatrix(seq.relative_odo(i, i + 1)) for i in range(5)]
+    eng, loader = runtime.get_engine(), runtime.get_loader()
+    runs = {}
+    for ahead in (True, False):
+        staged0, hits0 = loader.stats["staged"], loader.stats["staged_hits"]
+        saved = loader.stage_ahead
+        if not ahead:
+            loader.stage_ahead = lambda *a, **k: None
+        try:
+            km = kfm_module.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icppointplane")
+            km.add_keyframe(0)
+            km.load_pointcloud(0)
+            km.pre_process(0)
+            Ts, clouds = [], []
+            for i in range(5):
+                km.add_keyframe(i + 1)
+                km.load_pointcloud(i + 1)
+                launches = eng.kernel_launches()
+                km.pre_process(i + 1)
+                if ahead and i >= 1:
+                    assert eng.kernel_launches() == launches          # the work was done ahead: nothing left to launch
+                Ts.append(km.compute_transformation(i, i + 1, Tij=odo[i]).array.copy())
+                pc = km.keyframes[i + 1].pointcloud_filtered
+                clouds.append((pc.points.copy(), pc.normals.copy()))
+                km.unload_pointcloud(i)
+            km.unload_pointcloud(5)
+        finally:
+            loader.stage_ahead = saved
+        runs[ahead] = (np.array(Ts), clouds)
+        if ahead:
+            assert loader.stats["staged"] - staged0 == 4 and loader.stats["staged_hits"] - hits0 == 4 and not loader.staged
+    np.testing.assert_array_equal(runs[True][0], runs[False][0])
+    for (pa, na), (pb, nb) in zip(runs[True][1], runs[False][1]):
+        np.testing.assert_array_equal(pa, pb)
+        np.testing.assert_array_equal(na, nb)
+    pre = [orc.preprocess(seq.scans[k]) for k in (2, 3)]
+    ref = orc.icp(pre[1][0], pre[0][0], pre[0][1], odo[2].array, orc.P2PLANE)
+    assert np.abs(runs[True][0][2] - ref.transformation).max() < 1e-4
+
+
+def test_preprocess_ahead_overlaps_a_running_batch_and_matches_the_plain_call():
+    """C-ABI level: arvc_scan_preprocess_ahead, issued while a long registration batch occupies the context stream, completes
+    before that batch does (it runs on its own stream) and leaves exactly the device state arvc_scan_preprocess produces."""
+    import time
+    seq = synth.Sequence(3, synth.OS1_64, start=30.0)
+    eng = runtime.get_engine()
+    pp, ip = eng.make_preprocess_params(), eng.make_icp_params()
+    for k in range(3):
+        eng.upload(900 + k, seq.scans[k])
+    eng.upload(910, seq.scans[2])
+    eng.preprocess([900, 901, 910], pp)
+    want_pts, want_nrm = eng.get_points(910, normals=True)
+    n_rep = 300
+    init = np.repeat(seq.relative_odo(0, 1)[None], n_rep, axis=0)
+    eng.icp_batch([900] * n_rep, [901] * n_rep, init, ip)             # warm: graph instantiated
+    eng.sync()
+    t0 = time.perf_counter()
+    ticket = eng.icp_batch_async([900] * n_rep, [901] * n_rep, init, ip)
+    eng.preprocess_ahead([902], pp)
+    t_enq = time.perf_counter() - t0
+    rec = eng.icp_batch_finish(ticket)
+    t_icp = time.perf_counter() - t0
+    assert t_enq < 0.5 * t_icp, (t_enq, t_icp)                        # the call only enqueues
+    got_pts, got_nrm = eng.get_points(902, normals=True)              # ordered after the look-ahead job
+    np.testing.assert_array_equal(got_pts, want_pts)
+    np.testing.assert_array_equal(got_nrm, want_nrm)
+    launches = eng.kernel_launches()
+    eng.preprocess([902], pp)                                         # same parameters: found done
+    assert eng.kernel_launches() == launches
+    r1 = eng.icp_batch([901], [902], seq.relative_odo(1, 2)[None], ip)[0]
+    r2 = eng.icp_batch([901], [910], seq.relative_odo(1, 2)[None], ip)[0]
+    np.testing.assert_array_equal(r1["T"], r2["T"])
+    assert (rec["updates"] == rec["updates"][0]).all()
+    # a scan that already holds preprocessed state takes the ordinary path (nothing on the main stream may be using it)
+    eng.invalidate([902])
+    eng.preprocess_ahead([902], pp)
+    np.testing.assert_array_equal(eng.get_points(902), want_pts)
+    for k in (900, 901, 902, 910):
+        eng.free(k)
+
+
 def test_icp2planes_method(kfm_module, tmp_path):
     """'icp2planes' through the drop-in (keyframe.py:164-189, 262-295): preprocess -> plane -> split -> two point-to-plane
     registrations in one batch -> component merge, against the same pipeline on the oracle."""
