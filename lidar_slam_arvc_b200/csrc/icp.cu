@@ -43,6 +43,9 @@ constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
 constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may hold
+#ifndef ARVC_SEARCH_OCC
+#define ARVC_SEARCH_OCC 8  // resident blocks per SM the search kernel is compiled for (register budget)
+#endif
 #ifndef ARVC_SCANCAP
 #define ARVC_SCANCAP 1024
 #endif
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(256) k_icp_select(const BatchDesc* __restrict_
 }
 
 template <bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock) k_icp_search(const BatchDesc* __restrict__ bd) {
+__global__ void __launch_bounds__(kIcpBlock, ARVC_SEARCH_OCC) k_icp_search(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
