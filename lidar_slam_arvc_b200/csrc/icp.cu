@@ -46,6 +46,10 @@ constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may 
 #ifndef ARVC_SEARCH_OCC
 #define ARVC_SEARCH_OCC 8  // resident blocks per SM the search kernel is compiled for (register budget)
 #endif
+#ifndef ARVC_FARSH0
+#define ARVC_FARSH0 99     // far grid: no shrinking with the passes (measured: tails dominate)
+#define ARVC_FARSH1 99
+#endif
 #ifndef ARVC_SCANCAP
 #define ARVC_SCANCAP 1024
 #endif
@@ -58,7 +62,10 @@ constexpr int kStage = ARVC_STAGE;        // records staged in shared memory per
 #ifndef ARVC_STAGE_BULK
 #define ARVC_STAGE_BULK 0
 #endif
-constexpr int kFarBlocks = 296;   // blocks per pair of the far-query kernel (2 x 148 SMs)
+#ifndef ARVC_FARBLOCKS
+#define ARVC_FARBLOCKS 296
+#endif
+constexpr int kFarBlocks = ARVC_FARBLOCKS;   // blocks per pair of the far-query kernel (2 x 148 SMs)
 constexpr int kSpreadBlocks = 3552;   // three waves of search blocks (148 SMs x 8 resident): below that, queries are spread thinner
 
 __device__ __forceinline__ double box_d2(const GridSpec& g, int cx, int cy, int cz, double cl, double sx, double sy, double sz) {
@@ -1137,7 +1144,8 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
     // far queries: a few per cent of the points; 296 blocks x 8 groups per pair stride over the pair's far list
-    const dim3 gfar(kFarBlocks * mult, n_pairs_grid);
+    const int sh_far = pass < ARVC_FARSH0 ? 0 : (pass < ARVC_FARSH1 ? 1 : 2);      // far lists shrink with the passes
+    const dim3 gfar((kFarBlocks >> sh_far) * mult, n_pairs_grid);
     static char far_names[64][16];
     snprintf(far_names[pass < 63 ? pass : 63], 16, "icp_far_%02d", pass < 63 ? pass : 63);
     const char* fn = far_names[pass < 63 ? pass : 63];
