@@ -43,9 +43,18 @@ constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
 constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may hold
+// resident blocks per SM the search / far-query kernels are compiled for (register budgets: 8 -> 121, 10 -> 96, 16 -> 64
+// registers per thread); the _DENSE builds serve batches of kDenseBatch pairs or more
 #ifndef ARVC_SEARCH_OCC
-#define ARVC_SEARCH_OCC 8  // resident blocks per SM the search kernel is compiled for (register budget)
+#define ARVC_SEARCH_OCC 8
 #endif
+#ifndef ARVC_SEARCH_OCC_DENSE
+#define ARVC_SEARCH_OCC_DENSE 10
+#endif
+#ifndef ARVC_DENSE_BATCH
+#define ARVC_DENSE_BATCH 64
+#endif
+constexpr int kDenseBatch = ARVC_DENSE_BATCH;
 #ifndef ARVC_FARSH0
 #define ARVC_FARSH0 99     // far grid: no shrinking with the passes (measured: tails dominate)
 #define ARVC_FARSH1 99
@@ -61,6 +70,12 @@ constexpr int kUnionMax = 64;    // most cells a group's union may span (<= 2 * 
 constexpr int kStage = ARVC_STAGE;        // records staged in shared memory per group and round
 #ifndef ARVC_STAGE_BULK
 #define ARVC_STAGE_BULK 0
+#endif
+#ifndef ARVC_FAR_OCC
+#define ARVC_FAR_OCC 1
+#endif
+#ifndef ARVC_FAR_OCC_DENSE
+#define ARVC_FAR_OCC_DENSE 16
 #endif
 #ifndef ARVC_FARBLOCKS
 #define ARVC_FARBLOCKS 296
@@ -442,8 +457,8 @@ __global__ void __launch_bounds__(256) k_icp_select(const BatchDesc* __restrict_
     }   // chunk loop
 }
 
-template <bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock, ARVC_SEARCH_OCC) k_icp_search(const BatchDesc* __restrict__ bd) {
+template <bool SW, bool TW, int OCC>
+__global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_search(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ float4 s_stage[kGroupsPerBlock][kStage];
@@ -846,8 +861,8 @@ __global__ void __launch_bounds__(kIcpBlock, ARVC_SEARCH_OCC) k_icp_search(const
 
 // Far queries of a pass (their nearest neighbour lies beyond the cells the shared-candidate phase covers): one 8-lane
 // group per far-list entry, cooperative branch and bound over the coarser levels, groups striding over the list.
-template <bool SW, bool TW>
-__global__ void __launch_bounds__(kIcpBlock) k_icp_far(const BatchDesc* __restrict__ bd) {
+template <bool SW, bool TW, int OCC>
+__global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_far(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
     __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
@@ -1139,20 +1154,23 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
         if (combos_mask & 4) E.kernel("icp_select", (const void*)k_icp_select<true, false>, g256, dim3(256), args);
         if (combos_mask & 8) E.kernel("icp_select", (const void*)k_icp_select<true, true>, g256, dim3(256), args);
     }
-    if (combos_mask & 1) E.kernel(nm, (const void*)k_icp_search<false, false>, gsearch, dim3(kIcpBlock), args);
-    if (combos_mask & 2) E.kernel(nm, (const void*)k_icp_search<false, true>, gsearch, dim3(kIcpBlock), args);
-    if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false>, gsearch, dim3(kIcpBlock), args);
-    if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true>, gsearch, dim3(kIcpBlock), args);
+    // Large batches are throughput bound - more resident warps pay for a few spilled registers; small ones (the 12 pairs of
+    // a 128-beam step, one pair per call) are latency bound and want the spill-free build.  Float32 records only.
+    const bool dense_batch = n_pairs_grid >= kDenseBatch;
+    if (combos_mask & 1) E.kernel(nm, dense_batch ? (const void*)k_icp_search<false, false, ARVC_SEARCH_OCC_DENSE> : (const void*)k_icp_search<false, false, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel(nm, (const void*)k_icp_search<false, true, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel(nm, (const void*)k_icp_search<true, true, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
     // far queries: a few per cent of the points; 296 blocks x 8 groups per pair stride over the pair's far list
     const int sh_far = pass < ARVC_FARSH0 ? 0 : (pass < ARVC_FARSH1 ? 1 : 2);      // far lists shrink with the passes
     const dim3 gfar((kFarBlocks >> sh_far) * mult, n_pairs_grid);
     static char far_names[64][16];
     snprintf(far_names[pass < 63 ? pass : 63], 16, "icp_far_%02d", pass < 63 ? pass : 63);
     const char* fn = far_names[pass < 63 ? pass : 63];
-    if (combos_mask & 1) E.kernel(fn, (const void*)k_icp_far<false, false>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 2) E.kernel(fn, (const void*)k_icp_far<false, true>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 4) E.kernel(fn, (const void*)k_icp_far<true, false>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 8) E.kernel(fn, (const void*)k_icp_far<true, true>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 1) E.kernel(fn, dense_batch ? (const void*)k_icp_far<false, false, ARVC_FAR_OCC_DENSE> : (const void*)k_icp_far<false, false, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel(fn, (const void*)k_icp_far<false, true, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel(fn, (const void*)k_icp_far<true, false, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel(fn, (const void*)k_icp_far<true, true, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 1) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), args);
