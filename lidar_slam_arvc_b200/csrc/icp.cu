@@ -1156,7 +1156,8 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     }
     // Large batches are throughput bound - more resident warps pay for a few spilled registers; small ones (the 12 pairs of
     // a 128-beam step, one pair per call) are latency bound and want the spill-free build.  Float32 records only.
-    const bool dense_batch = n_pairs_grid >= kDenseBatch;
+    static const int dense_min = getenv("ARVC_DENSE_BATCH") ? atoi(getenv("ARVC_DENSE_BATCH")) : kDenseBatch;   // profiling knob
+    const bool dense_batch = n_pairs_grid >= dense_min;
     if (combos_mask & 1) E.kernel(nm, dense_batch ? (const void*)k_icp_search<false, false, ARVC_SEARCH_OCC_DENSE> : (const void*)k_icp_search<false, false, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel(nm, (const void*)k_icp_search<false, true, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel(nm, (const void*)k_icp_search<true, false, ARVC_SEARCH_OCC>, gsearch, dim3(kIcpBlock), args);
