@@ -198,6 +198,10 @@ long long arvc_lzf_decompress(const unsigned char* in, size_t n_in, unsigned cha
 /* pinned host staging (optional; plain malloc'ed pointers work too, just slower for H2D) */
 void* arvc_host_alloc(size_t bytes);
 void* arvc_ctx_host_alloc(arvc_ctx* ctx, size_t bytes);   /* same, after selecting the context's device (for helper threads) */
+/* Optional: grow the device memory pool by `bytes` now.  Scans and batches allocate from that pool; when it has to grow
+ * while kernels run, the allocating call waits for them.  A caller that knows its footprint (loop closing keeps every
+ * visited keyframe resident - loopclosing.py:163-178 never unloads - at ~12 MB per 64-beam scan) reserves it up front. */
+int arvc_ctx_reserve(arvc_ctx* ctx, size_t bytes);
 void arvc_host_free(void* p);
 
 #ifdef __cplusplus

@@ -294,6 +294,7 @@ int arvc_ctx_create(int device, arvc_ctx** out) {
     // kernels) are scheduled before the blocks of the next scan's preprocessing, which only fills the gaps
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (getenv("ARVC_STREAM_PRIO") && atoi(getenv("ARVC_STREAM_PRIO")) == 0) prio_greatest = prio_least = 0;      // A/B knob
     e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->L.stream, cudaStreamNonBlocking, prio_greatest);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->ahead_stream, cudaStreamNonBlocking, prio_least);
@@ -1138,5 +1139,19 @@ void* arvc_ctx_host_alloc(arvc_ctx* ctx, size_t bytes) {
     return arvc_host_alloc(bytes);
 }
 void arvc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int arvc_ctx_reserve(arvc_ctx* ctx, size_t bytes) {
+    if (!ctx) return ARVC_E_ARG;
+    CK((cudaError_t)ctx->enter());
+    if (bytes == 0) return ARVC_OK;
+    // one allocation of that size, given straight back: the device's memory pool keeps it (release threshold = max), and
+    // later per-scan / per-batch allocations are carved out of it instead of growing the pool while kernels run
+    void* p = nullptr;
+    const cudaError_t e = cudaMallocAsync(&p, bytes, ctx->L.stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx->fail(ARVC_E_NOMEM, "ctx_reserve: device allocation failed"); }
+    CK(cudaFreeAsync(p, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return ARVC_OK;
+}
 
 }  // extern "C"

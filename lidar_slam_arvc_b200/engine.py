@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "arvc_scan_get_nn_counts", "arvc_icp_batch", "arvc_icp_batch_async", "arvc_icp_batch_finish", "arvc_icp_trace",
     "arvc_host_alloc", "arvc_host_free", "arvc_profile_enable", "arvc_profile_report", "arvc_scan_invalidate", "arvc_lzf_decompress",
     "arvc_map_build", "arvc_scan_fit_plane", "arvc_scan_split_plane", "arvc_ctx_set_option", "arvc_scan_get_counters",
-    "arvc_icp_batch_device_records", "arvc_scan_wait_upload", "arvc_ctx_host_alloc", "arvc_scan_get_neighbors",
+    "arvc_icp_batch_device_records", "arvc_scan_wait_upload", "arvc_ctx_host_alloc", "arvc_ctx_reserve", "arvc_scan_get_neighbors",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     lib.arvc_host_alloc.restype = vp
     lib.arvc_ctx_host_alloc.argtypes = [vp, c.c_size_t]
     lib.arvc_ctx_host_alloc.restype = vp
+    lib.arvc_ctx_reserve.argtypes = [vp, c.c_size_t]
     lib.arvc_host_free.argtypes = [vp]
     lib.arvc_host_free.restype = None
     _lib = lib
@@ -257,6 +258,10 @@ class Engine:
     def preprocess(self, scan_ids, params):
         ids = np.ascontiguousarray(scan_ids, dtype=np.int64).reshape(-1)
         self._ck(self.lib.arvc_scan_preprocess(self.h, len(ids), _i64p(ids), ctypes.byref(params)))
+
+    def reserve(self, n_bytes):
+        """Grow the device memory pool now (arvc_ctx_reserve) instead of piecemeal while kernels run."""
+        self._ck(self.lib.arvc_ctx_reserve(self.h, ctypes.c_size_t(int(n_bytes))))
 
     def preprocess_ahead(self, scan_ids, params):
         """preprocess() of scans needed next, on the engine's look-ahead stream (overlaps a registration in flight)."""

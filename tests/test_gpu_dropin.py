@@ -367,3 +367,21 @@ def test_icp2planes_method(kfm_module, tmp_path):
         assert np.linalg.norm(single[i].array[:3, 3] - seq.relative_gt(i, i + 1)[:3, 3]) < 0.05
     km.unload_pointcloud(0)
     assert km.keyframes[0].pointcloud_ground_plane is None
+
+
+def test_reserve_grows_the_pool_and_fails_cleanly():
+    """arvc_ctx_reserve: a reservation that fits succeeds; one that cannot fit reports ARVC_E_NOMEM and leaves the context
+    usable (the failed allocation must not stick as a CUDA error)."""
+    from lidar_slam_arvc_b200.engine import EngineError
+    eng = runtime.get_engine()
+    eng.reserve(256 << 20)
+    with pytest.raises(EngineError):
+        eng.reserve(1 << 50)
+    seq = synth.Sequence(2, synth.TINY_16, start=30.0)
+    for k in range(2):
+        eng.upload(950 + k, seq.scans[k])
+    eng.preprocess([950, 951], eng.make_preprocess_params())
+    rec = eng.icp_batch([950], [951], seq.relative_odo(0, 1)[None], eng.make_icp_params())[0]
+    assert rec["fitness"] > 0.9
+    for k in (950, 951):
+        eng.free(k)
