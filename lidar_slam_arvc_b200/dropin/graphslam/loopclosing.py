@@ -159,13 +159,15 @@ class LoopClosing():
         return rest[ok[0]] if len(ok) else None
 
     def store_positions(self):
+        # loopclosing.py:202-211 wraps every pose in a HomogeneousMatrix to read its position: the translation column of the
+        # 4x4 is the same three numbers without the ~250 k temporary objects of a 5 000-keyframe run
         est = self.graphslam.current_estimate
         poses = []
         i = 0
         while est.exists(i):
-            poses.append(_H(est.atPose3(i).matrix()).pos())
+            poses.append(np.asarray(est.atPose3(i).matrix(), dtype=np.float64)[0:3, 3])
             i += 1
-        self.positions = np.array(poses)
+        self.positions = np.array(poses).reshape(-1, 3)
 
     def find_candidates(self):
         self.store_positions()
