@@ -477,12 +477,15 @@ __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_search(const BatchDesc* 
 
     if ((int)blockIdx.y >= bd->n_pairs) return;
     const PairDev& pr = bd->pairs[blockIdx.y];
-    const ScanDev& src = *pr.src;
-    const ScanDev& tgt = *pr.tgt;
-    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
     const int pass = st->passes;         // completed passes = index of this one
+    // a block beyond the work list has nothing to do whatever q turns out to be (a chunk holds at least kGroupsPerBlock
+    // entries): gone before it touches the scans
+    if (pass > 0 && (int)(blockIdx.x * kGroupsPerBlock) >= st->nlist) return;
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     struct { double max_d2, cert_margin; int debug; } ip = {bd->ip.max_d2, bd->ip.cert_margin, bd->ip.debug};
     const int n = pass == 0 ? src.counts[CNT_NPTS] : st->nlist;       // pass 0 searches every point
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
@@ -869,12 +872,13 @@ __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_far(const BatchDesc* __r
     __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
     if ((int)blockIdx.y >= bd->n_pairs) return;
     const PairDev& pr = bd->pairs[blockIdx.y];
-    const ScanDev& src = *pr.src;
-    const ScanDev& tgt = *pr.tgt;
-    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
     const int nfar = st->nfar;
+    if ((int)(blockIdx.x * kGroupsPerBlock) >= nfar) return;      // most blocks of a late pass: gone before they touch the scans
+    const ScanDev& src = *pr.src;
+    const ScanDev& tgt = *pr.tgt;
+    if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
     const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
     const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
     const double max_d2 = bd->ip.max_d2;
