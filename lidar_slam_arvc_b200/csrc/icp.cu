@@ -38,7 +38,10 @@ struct Best { double d2; int idx; int pos; };
 // ---------------------------------------------------------------------------------------------------
 constexpr int kG = 8;            // lanes per query (16: unions outgrow the caps, 15x slower)
 constexpr unsigned kGMask = kG == 32 ? 0xffffffffu : ((1u << kG) - 1u);
-constexpr int kBigRun = 160;     // longer runs are expanded into their children instead of scanned
+#ifndef ARVC_BIGRUN
+#define ARVC_BIGRUN 160
+#endif
+constexpr int kBigRun = ARVC_BIGRUN;     // longer runs are expanded into their children instead of scanned
 constexpr int kStack = 48;       // stack entries per group
 constexpr int kGroupsPerBlock = kIcpBlock / kG;
 constexpr int kUnionLevels = 5;  // finest levels the shared-candidate (union) phase may use (coarse ones only where sparse)
@@ -77,6 +80,9 @@ constexpr int kStage = ARVC_STAGE;        // records staged in shared memory per
 #ifndef ARVC_FAR_OCC_DENSE
 #define ARVC_FAR_OCC_DENSE 16
 #endif
+#ifndef ARVC_FAR_G
+#define ARVC_FAR_G 8      // lanes per query in the far kernel
+#endif
 #ifndef ARVC_FARBLOCKS
 #define ARVC_FARBLOCKS 296
 #endif
@@ -103,7 +109,7 @@ struct ScreenThr {
     __device__ __forceinline__ float operator()(double best_d2) const { return fmaf(__double2float_ru(best_d2), k1, k0); }
 };
 
-template <bool TW>
+template <bool TW, int G, int STK>
 __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, double sy, double sz, double in_d2, int in_idx, int level,
                                              Best& lb, uint4* __restrict__ stk, float* __restrict__ stk_lb, int gl,
                                              unsigned gmask) {
@@ -112,7 +118,8 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
     const HashEntry* __restrict__ tab = tgt.table;
     const unsigned tmask = tgt.table_mask;
     const GridSpec g = tgt.grid;
-    const int gshift = (lane_id() / kG) * kG;
+    const int gshift = (lane_id() / G) * G;
+    constexpr unsigned kMaskG = G >= 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     const float sxf = (float)sx, syf = (float)sy, szf = (float)sz;
     const float e = (float)(fmax(fabs(sx), fmax(fabs(sy), fabs(sz))) * 6.0e-8 + 1e-30);
     double gbest = in_d2;                       // group-wide best d2 (every lane holds the same value)
@@ -134,7 +141,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
         const CellDecoder dec(nx, ny);
         int top = 0;
         // push the ball's cells, later rounds first, so that order position 0 (the home cell) ends on top
-        for (int base = ((ncell - 1) / kG) * kG; base >= 0; base -= kG) {
+        for (int base = ((ncell - 1) / G) * G; base >= 0; base -= G) {
             const int t = base + gl;
             bool valid = false;
             unsigned st = 0, en = 0;
@@ -150,7 +157,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                     lbf = __double2float_rd(bd);
                 }
             }
-            const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kGMask;
+            const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kMaskG;
             if (valid) {
                 const int pos = top + __popc(vm & ~((2u << gl) - 1u));
                 stk[pos] = make_uint4(st, en, (unsigned)cx | ((unsigned)cy << 10) | ((unsigned)cz << 20), (unsigned)l);
@@ -167,29 +174,26 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
             if ((double)lbf > gbest * (1.0 + 1e-9) + 1e-12) continue;
             const int el = (int)en4.w;
             const unsigned cnt = en4.y - en4.x;
-            if (el == 0 || cnt <= (unsigned)kBigRun || top + 8 > kStack) {
+            if (el == 0 || cnt <= (unsigned)kBigRun || top + 8 > STK) {
                 if constexpr (!TW) {
-                    for (unsigned p0 = en4.x + gl; p0 < en4.y; p0 += 4 * kG) {      // four loads in flight per lane
-                        float4 v4[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned p = p0 + u * kG;
-                            v4[u] = p < en4.y ? __ldg(reinterpret_cast<const float4*>(recs + p)) : make_float4(INFINITY, 0.f, 0.f, 0.f);
+                    const float4* __restrict__ r4 = reinterpret_cast<const float4*>(recs);
+                    auto eval = [&](const float4& v, unsigned p) {
+                        const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
+                        const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (d2f <= thr) {
+                            const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
+                            const int idx = __float_as_int(v.w);
+                            if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)p; thr = screen_thr(d2); }
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float4 v = v4[u];
-                            const float dx = sxf - v.x, dy = syf - v.y, dz = szf - v.z;
-                            const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (d2f <= thr) {
-                                const double d2 = sqdist(sx, sy, sz, (double)v.x, (double)v.y, (double)v.z);
-                                const int idx = __float_as_int(v.w);
-                                if (d2 < lb.d2 || (d2 == lb.d2 && idx < lb.idx)) { lb.d2 = d2; lb.idx = idx; lb.pos = (int)(p0 + u * kG); thr = screen_thr(d2); }
-                            }
-                        }
+                    };
+                    unsigned p0 = en4.x + gl;
+                    for (; p0 + 3 * G < en4.y; p0 += 4 * G) {      // four loads in flight per lane, no bounds tests in the bulk
+                        const float4 a = __ldg(r4 + p0), b = __ldg(r4 + p0 + G), c = __ldg(r4 + p0 + 2 * G), d = __ldg(r4 + p0 + 3 * G);
+                        eval(a, p0); eval(b, p0 + G); eval(c, p0 + 2 * G); eval(d, p0 + 3 * G);
                     }
+                    for (; p0 < en4.y; p0 += G) eval(__ldg(r4 + p0), p0);
                 }
-                for (unsigned p = en4.x + gl; TW && p < en4.y; p += kG) {
+                for (unsigned p = en4.x + gl; TW && p < en4.y; p += G) {
                     if constexpr (!TW) {
                     } else {
                         double x, y, z;
@@ -202,7 +206,7 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                 // share the bound: group-wide minimum of the lanes' best distances
                 double m = lb.d2;
 #pragma unroll
-                for (int o = kG / 2; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(gmask, m, o, kG));
+                for (int o = G / 2; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(gmask, m, o, G));
                 if (m < gbest) { gbest = m; thr = fminf(thr, screen_thr(m)); }
             } else {
                 // expand into the eight children, lane r <-> r-th nearest octant
@@ -210,19 +214,24 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
                 const double pcl = g.c0 * (double)(1 << el), h = 0.5 * pcl;
                 const unsigned near = ((sx >= g.ox + cx * pcl + h) ? 4u : 0u) | ((sy >= g.oy + cy * pcl + h) ? 2u : 0u) |
                                       ((sz >= g.oz + cz * pcl + h) ? 1u : 0u);
-                const unsigned child = near ^ ((0x76534210u >> (4 * gl)) & 7u);      // 0,1,2,4,3,5,6,7 axis flips
-                const int ccx = 2 * cx + (int)((child >> 2) & 1u), ccy = 2 * cy + (int)((child >> 1) & 1u), ccz = 2 * cz + (int)(child & 1u);
-                const double bd = box_d2(g, ccx, ccy, ccz, h, sx, sy, sz);
-                bool valid = false;
-                unsigned st = 0, en = 0;
-                if (bd <= gbest * (1.0 + 1e-9) + 1e-12) valid = grid_lookup(tab, tmask, el - 1, morton3(ccx, ccy, ccz), st, en);
-                const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kGMask;
-                if (valid) {
-                    const int pos = top + __popc(vm & ~((2u << gl) - 1u));
-                    stk[pos] = make_uint4(st, en, (unsigned)ccx | ((unsigned)ccy << 10) | ((unsigned)ccz << 20), (unsigned)(el - 1));
-                    stk_lb[pos] = __double2float_rd(bd);
+                // rounds of G octants, farthest first, so that the nearest octant ends on top of the stack
+#pragma unroll
+                for (int rnd = (8 + G - 1) / G - 1; rnd >= 0; --rnd) {
+                    const int r = rnd * G + gl;
+                    const unsigned child = near ^ ((0x76534210u >> (4 * (r & 7))) & 7u);      // 0,1,2,4,3,5,6,7 axis flips
+                    const int ccx = 2 * cx + (int)((child >> 2) & 1u), ccy = 2 * cy + (int)((child >> 1) & 1u), ccz = 2 * cz + (int)(child & 1u);
+                    const double bd = box_d2(g, ccx, ccy, ccz, h, sx, sy, sz);
+                    bool valid = false;
+                    unsigned st = 0, en = 0;
+                    if (r < 8 && bd <= gbest * (1.0 + 1e-9) + 1e-12) valid = grid_lookup(tab, tmask, el - 1, morton3(ccx, ccy, ccz), st, en);
+                    const unsigned vm = (__ballot_sync(gmask, valid) >> gshift) & kMaskG;
+                    if (valid) {
+                        const int pos = top + __popc(vm & ~((2u << gl) - 1u));
+                        stk[pos] = make_uint4(st, en, (unsigned)ccx | ((unsigned)ccy << 10) | ((unsigned)ccz << 20), (unsigned)(el - 1));
+                        stk_lb[pos] = __double2float_rd(bd);
+                    }
+                    top += __popc(vm);
                 }
-                top += __popc(vm);
                 __syncwarp(gmask);
             }
         }
@@ -231,10 +240,10 @@ __device__ __forceinline__ void group_search(const ScanDev& tgt, double sx, doub
     }
     // lexicographic (d2, index) minimum over the group; lanes that found nothing carry the incoming bound with pos = -1
 #pragma unroll
-    for (int o = kG / 2; o > 0; o >>= 1) {
-        const double od2 = __shfl_xor_sync(gmask, lb.d2, o, kG);
-        const int oidx = __shfl_xor_sync(gmask, lb.idx, o, kG);
-        const int opos = __shfl_xor_sync(gmask, lb.pos, o, kG);
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double od2 = __shfl_xor_sync(gmask, lb.d2, o, G);
+        const int oidx = __shfl_xor_sync(gmask, lb.idx, o, G);
+        const int opos = __shfl_xor_sync(gmask, lb.pos, o, G);
         if (od2 < lb.d2 || (od2 == lb.d2 && (oidx < lb.idx || (oidx == lb.idx && opos > lb.pos)))) { lb.d2 = od2; lb.idx = oidx; lb.pos = opos; }
     }
 }
@@ -868,25 +877,28 @@ template <bool SW, bool TW, int OCC>
 __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_far(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
-    __shared__ uint4 s_stk[kGroupsPerBlock][kStack];
-    __shared__ float s_stk_lb[kGroupsPerBlock][kStack];
+    constexpr int FG = ARVC_FAR_G;                       // lanes per far query
+    constexpr int kFarGroups = kIcpBlock / FG;
+    constexpr int kFarStack = FG >= 8 ? kStack : 40;     // 27 cells of a ball + one expansion fit; deeper stacks cost occupancy
+    __shared__ uint4 s_stk[kFarGroups][kFarStack];
+    __shared__ float s_stk_lb[kFarGroups][kFarStack];
     if ((int)blockIdx.y >= bd->n_pairs) return;
     const PairDev& pr = bd->pairs[blockIdx.y];
     const PairState* __restrict__ st = pr.state;
     if (st->done) return;
     const int nfar = st->nfar;
-    if ((int)(blockIdx.x * kGroupsPerBlock) >= nfar) return;      // most blocks of a late pass: gone before they touch the scans
+    if ((int)(blockIdx.x * kFarGroups) >= nfar) return;      // most blocks of a late pass: gone before they touch the scans
     const ScanDev& src = *pr.src;
     const ScanDev& tgt = *pr.tgt;
     if ((src.wide != 0) != SW || (tgt.wide != 0) != TW) return;
-    const int lane = lane_id(), gl = lane & (kG - 1), grp = threadIdx.x / kG;
-    const unsigned gmask = (kG == 32) ? kFull : (((1u << kG) - 1u) << (lane & ~(kG - 1)));
+    const int lane = lane_id(), gl = lane & (FG - 1), grp = threadIdx.x / FG;
+    const unsigned gmask = FG >= 32 ? kFull : (((1u << (FG & 31)) - 1u) << (lane & ~(FG - 1)));
     const double max_d2 = bd->ip.max_d2;
     double T[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->T[k];
 #pragma unroll 1
-    for (int f = blockIdx.x * kGroupsPerBlock + grp; f < nfar; f += gridDim.x * kGroupsPerBlock) {
+    for (int f = blockIdx.x * kFarGroups + grp; f < nfar; f += gridDim.x * kFarGroups) {
         const int e = pr.far_list[f];
         const int i = e & 0xffffff, level = e >> 24;
         double px, py, pz;
@@ -907,7 +919,7 @@ __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_far(const BatchDesc* __r
             if (d2 < bd2) { bd2 = d2; bidx = idx; }
         }
         Best lb;
-        group_search<TW>(tgt, sx, sy, sz, bd2, bidx, level, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
+        group_search<TW, FG, kFarStack>(tgt, sx, sy, sz, bd2, bidx, level, lb, s_stk[grp], s_stk_lb[grp], gl, gmask);
         if (gl == 0 && lb.pos >= 0) pr.prev[i] = lb.pos;      // else: nothing strictly better than the bound, prev[i] stands
         __syncwarp(gmask);
     }
