@@ -670,9 +670,8 @@ def config5_line(args, torch, engine, synth, eng):
     t_gen = time.perf_counter() - t0
     odo = [seq5.relative_odo(k, k + 1) for k in range(n5 - 1)]
     pin5 = pin_scans(torch, seq5.scans)
-    # loop closing never unloads (loopclosing.py:163-178): ~660 keyframes stay resident at ~12 MB each - reserve the pool's
-    # memory up front (arvc_ctx_reserve) instead of letting it grow piecemeal while batches run
-    eng.reserve(10 << 30)
+    # (no arvc_ctx_reserve here: this context's pool already holds the memory the earlier lines used; reserving on top of a
+    # populated pool was measured to slow the first batches down - it is for a fresh context)
     eng.sync()
     t0 = time.perf_counter()
     l0 = eng.kernel_launches()

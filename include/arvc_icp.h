@@ -200,7 +200,9 @@ void* arvc_host_alloc(size_t bytes);
 void* arvc_ctx_host_alloc(arvc_ctx* ctx, size_t bytes);   /* same, after selecting the context's device (for helper threads) */
 /* Optional: grow the device memory pool by `bytes` now.  Scans and batches allocate from that pool; when it has to grow
  * while kernels run, the allocating call waits for them.  A caller that knows its footprint (loop closing keeps every
- * visited keyframe resident - loopclosing.py:163-178 never unloads - at ~12 MB per 64-beam scan) reserves it up front. */
+ * visited keyframe resident - loopclosing.py:163-178 never unloads - at ~12 MB per 64-beam scan) reserves it up front:
+ * once, right after arvc_ctx_create.  (On a pool that already holds memory it does not help: the first batches after it
+ * were measured slower.) */
 int arvc_ctx_reserve(arvc_ctx* ctx, size_t bytes);
 void arvc_host_free(void* p);
 
