@@ -105,6 +105,9 @@ def test_sequential_caller_gets_the_next_scan_preprocessed_ahead(tmp_path):
             ld = runtime.get_loader()
             if not ahead:
                 ld.stage_ahead = lambda *a, **k: None
+            else:
+                patient = ld.stage_ahead                 # the product waits 0.5 ms for the read-ahead thread and otherwise skips
+                ld.stage_ahead = lambda alloc: patient(alloc, wait_s=10.0)      # the look-ahead; a test must not depend on that race
             km = kfm.KeyFrameManager(directory=d, scan_times=times, voxel_size=None, method="icppointplane")
             km.add_keyframe(0)
             km.load_pointcloud(0)
