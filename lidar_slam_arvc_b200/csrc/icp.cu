@@ -873,11 +873,10 @@ __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_search(const BatchDesc* 
 
 // Far queries of a pass (their nearest neighbour lies beyond the cells the shared-candidate phase covers): one 8-lane
 // group per far-list entry, cooperative branch and bound over the coarser levels, groups striding over the list.
-template <bool SW, bool TW, int OCC>
+template <bool SW, bool TW, int OCC, int FG /* lanes per far query */>
 __global__ void __launch_bounds__(kIcpBlock, OCC) k_icp_far(const BatchDesc* __restrict__ bd) {
     typedef typename RecT<SW>::type SRec;
     typedef typename RecT<TW>::type TRec;
-    constexpr int FG = ARVC_FAR_G;                       // lanes per far query
     constexpr int kFarGroups = kIcpBlock / FG;
     constexpr int kFarStack = FG >= 8 ? kStack : 40;     // 27 cells of a ball + one expansion fit; deeper stacks cost occupancy
     __shared__ uint4 s_stk[kFarGroups][kFarStack];
@@ -1184,10 +1183,16 @@ void emit_pass(Emitter& E, const BatchDesc* d_bd, int gx_search, int cap_max, in
     static char far_names[64][16];
     snprintf(far_names[pass < 63 ? pass : 63], 16, "icp_far_%02d", pass < 63 ? pass : 63);
     const char* fn = far_names[pass < 63 ? pass : 63];
-    if (combos_mask & 1) E.kernel(fn, dense_batch ? (const void*)k_icp_far<false, false, ARVC_FAR_OCC_DENSE> : (const void*)k_icp_far<false, false, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 2) E.kernel(fn, (const void*)k_icp_far<false, true, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 4) E.kernel(fn, (const void*)k_icp_far<true, false, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
-    if (combos_mask & 8) E.kernel(fn, (const void*)k_icp_far<true, true, ARVC_FAR_OCC>, gfar, dim3(kIcpBlock), args);
+    // one or two pairs per call (the reference's own loop): a pass is as long as its slowest far query, so the whole warp
+    // serves one query (scans 4x as wide; 0.89 -> 0.83 ms per sequential pair); larger batches are throughput bound, where
+    // 8-lane groups do the least total work
+    const bool tiny_batch = n_pairs_grid <= 2;
+    if (combos_mask & 1) E.kernel(fn, tiny_batch ? (const void*)k_icp_far<false, false, ARVC_FAR_OCC, 32>
+                                      : dense_batch ? (const void*)k_icp_far<false, false, ARVC_FAR_OCC_DENSE, ARVC_FAR_G>
+                                                    : (const void*)k_icp_far<false, false, ARVC_FAR_OCC, ARVC_FAR_G>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 2) E.kernel(fn, (const void*)k_icp_far<false, true, ARVC_FAR_OCC, ARVC_FAR_G>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 4) E.kernel(fn, (const void*)k_icp_far<true, false, ARVC_FAR_OCC, ARVC_FAR_G>, gfar, dim3(kIcpBlock), args);
+    if (combos_mask & 8) E.kernel(fn, (const void*)k_icp_far<true, true, ARVC_FAR_OCC, ARVC_FAR_G>, gfar, dim3(kIcpBlock), args);
     if (combos_mask & 1) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, false>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 2) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, false, true>, gacc, dim3(kIcpBlock), args);
     if (combos_mask & 4) E.kernel("icp_accum", (const void*)k_icp_accum<METHOD, true, false>, gacc, dim3(kIcpBlock), args);
