@@ -55,7 +55,7 @@ constexpr int kUnionCandCap = 1024;   // most records a union at level >= 2 may 
 #define ARVC_SEARCH_OCC_DENSE 10
 #endif
 #ifndef ARVC_DENSE_BATCH
-#define ARVC_DENSE_BATCH 64
+#define ARVC_DENSE_BATCH 24
 #endif
 constexpr int kDenseBatch = ARVC_DENSE_BATCH;
 #ifndef ARVC_FARSH0

@@ -396,7 +396,7 @@ def test_loop_closure_batch_properties(eng):
     merged = np.concatenate(parts)
     np.testing.assert_array_equal(merged["T"], res["T"])
     np.testing.assert_array_equal(merged["rmse"], res["rmse"])
-    # batches of 64 pairs and more run the search / far-query kernels compiled for more resident blocks (other register
+    # batches of 24 pairs and more run the search / far-query kernels compiled for more resident blocks (other register
     # budgets, same source): the list twice over is such a batch, and every result is the same bit for bit
     big = eng.icp_batch(np.tile(tg, 2), np.tile(sr, 2), np.tile(init, (2, 1, 1)), ip)
     for half in (big[:len(tg)], big[len(tg):]):
